@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- instance-timesteps/s of the batched transient engine on B200.
+
+One "step" = one batched transient (load -> operating point -> every timestep
+of every instance) over one batch of synthetic parameter sets of the workload.
+Default workload: BASELINE.json configs[1], the half-wave diode rectifier with
+RC load, 10k-instance R/C sweep, per GPU (weak scaling: every rank runs its own
+10k-instance shard with a different seed offset; instances are independent, so
+there is no data-path collective).
+
+  value     accepted instance-timesteps of all ranks / device time, inputs
+            already resident in HBM (CUDA events on the launching stream, max
+            over ranks)
+  e2e       the same through the reference-facing C-ABI calls with HOST
+            buffers: per-instance parameters copied host->device and the
+            gridded probe waveforms + status copied device->host every step
+  roofline  transient kernel: SURVEY.md 8d algorithmic bytes per accepted
+            instance-timestep x timesteps / kernel time, vs measured HBM peak
+  cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, one
+            process per core, on a bounded sample of the same sweep
+
+`--impl reference` times only that CPU reference arm.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "instance-timesteps/sec batched transient"
+UNIT = "instance-timesteps/s"
+
+
+# ---------------------------------------------------------------------------
+# CPU reference arm (test infrastructure: oracle/_ref, else the oracle port)
+# ---------------------------------------------------------------------------
+def _cpu_worker(args):
+    name, M, indices, budget_s, use_ref = args
+    import backends
+    import workloads
+    w = workloads.make(name, M)
+    steps = n = 0
+    t0 = time.perf_counter()
+    for i in indices:
+        nl, s = w.instance_netlist(int(i))
+        sim = backends.RefSim(nl, s) if use_ref else backends.OracleSim(nl, s)
+        data, _ = sim.tran(w.tstep, w.tstop)
+        steps += data.shape[0] - 1
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return steps, n, time.perf_counter() - t0
+
+
+def cpu_reference_rate(name, M, budget_s, pool=None, cores=None):
+    """(instance-timesteps/s, cores, kind, sample text) of the CPU arm."""
+    import backends
+    backends.build_oracle()
+    use_ref = backends.ref_available()
+    cores = cores or len(os.sched_getaffinity(0))
+    rng = np.random.default_rng(7)
+    order = rng.permutation(M)
+    chunks = [order[c::cores][:4096] for c in range(cores)]
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores)
+    try:
+        res = pool.map(_cpu_worker, [(name, M, ch, budget_s, use_ref) for ch in chunks])
+    finally:
+        if own:
+            pool.close()
+    steps = sum(r[0] for r in res)
+    n = sum(r[1] for r in res)
+    wall = max(r[2] for r in res)
+    kind = "reference" if use_ref else "port"
+    sample = "%d of %d instances of %s (random subset), %d processes, %.1f s" % (
+        n, M, name, cores, wall)
+    return steps / wall, cores, kind, sample
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = a.workload
+    import workloads
+    M = a.instances or workloads.DEFAULT_INSTANCES[name]
+    cores = len(os.sched_getaffinity(0))
+    pool = mp.get_context("spawn").Pool(cores)
+    rates = []
+    sample = kind = None
+    try:
+        for it in range(a.warmup + a.steps):
+            rate, cores, kind, sample = cpu_reference_rate(name, M, a.cpu_seconds, pool, cores)
+            if it >= a.warmup:
+                rates.append(rate)
+    finally:
+        pool.close()
+    value = float(np.mean(rates))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * a.cpu_seconds, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (name, workloads.DESCRIPTION[name]),
+                       "instances_per_gpu": M},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "per step: " + sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--instances", type=int, default=0, help="instances per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tpb", type=int, default=0)
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import workloads
+    from eispice_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local)
+    engine.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    name = a.workload
+    M = a.instances or workloads.DEFAULT_INSTANCES[name]
+    w = workloads.make(name, M, seed_offset=1000 * rank)
+    eng = engine.Engine(w.cct.netlist(), w.M)
+    if a.tpb:
+        eng.set_option("threads_per_block", a.tpb)
+    eng.set_params(w.params)
+    t0 = time.perf_counter()
+    eng.prepare(w.tstep, w.tstop, 0.0, w.probes)
+    eng.upload()
+    prepare_s = time.perf_counter() - t0
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    # -- device-resident timing ------------------------------------------------
+    for _ in range(a.warmup):
+        eng.run_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms = tran_ms = 0.0
+    launches = 0
+    accepted = 0
+    for _ in range(a.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        eng.run_device()                       # legacy default stream == torch's default
+        e1.record(stream)
+        e1.synchronize()
+        dev_ms += e0.elapsed_time(e1)
+        st = eng.stats()
+        tran_ms += st["tranMs"]
+        launches += st["kernelLaunches"]
+        accepted += st["accepted"]
+    barrier()
+    st = eng.stats()
+    failed = st["failed"]
+
+    # -- end to end: host buffers in, host buffers out ---------------------------
+    nprobes = len(w.probes)
+    out = torch.empty((w.M, eng.ngrid, nprobes), dtype=torch.float64).pin_memory().numpy()
+    status = torch.empty(w.M, dtype=torch.int32).pin_memory().numpy()
+    h2d = sum(np.asarray(v).size * (4 if k.endswith(".set") else 8) for k, v in w.params.items())
+    d2h = out.nbytes + status.nbytes
+    for _ in range(2):
+        eng.set_params(w.params)
+        eng.upload()
+        eng.run_device()
+        eng.fetch(out, status)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_accepted = 0
+    for _ in range(a.steps):
+        eng.set_params(w.params)               # host arrays -> the handle (as the binding does)
+        eng.upload()                           # host -> device
+        eng.run_device()
+        eng.fetch(out, status)                 # device -> host, [M][ngrid][nprobes] + status
+        e2e_accepted += eng.stats()["accepted"]
+        launches += eng.stats()["kernelLaunches"] + 1
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
+
+    # -- reduce over ranks -------------------------------------------------------
+    vals = torch.tensor([dev_ms, e2e_s, tran_ms], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([accepted, e2e_accepted, failed, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max, tran_ms_max = vals.tolist()
+    accepted_all, e2e_accepted_all, failed_all, launches_all = sums.tolist()
+
+    if rank == 0:
+        value = accepted_all / (dev_ms_max * 1e-3)
+        e2e_value = e2e_accepted_all / e2e_s_max
+        n_tlines = sum(1 for d in w.cct.netlist() if d[0] == "T")
+        balg, k = workloads.algorithmic_bytes(st, n_tlines, nprobes)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # per launch: this rank's accepted steps of ONE run x B_alg / tran kernel time
+        steps_per_launch = accepted / a.steps
+        achieved = balg * steps_per_launch / (tran_ms / a.steps * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": dev_ms_max / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (name, workloads.DESCRIPTION[name]),
+                       "instances_per_gpu": w.M, "unknowns": st["numUnknowns"],
+                       "nnzA": st["numNonzeros"], "nnzLU": st["numFactor"],
+                       "solves_per_timestep": round(k, 3),
+                       "timesteps_per_instance": round(accepted / a.steps / w.M, 1),
+                       "threads_per_block": st["threadsPerBlock"],
+                       "lu_workspace": "shared" if st["workspaceInShared"] else "global",
+                       "l2": "flushed between timed steps (256 MiB write)",
+                       "failed_instances": int(failed_all),
+                       "prepare_s": round(prepare_s, 3)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "simcuTranKernel",
+                         "bytes_per_instance_timestep": round(balg, 1),
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "clocks": clocks,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                rate, cores, kind, sample = cpu_reference_rate(name, w.M, a.cpu_seconds)
+                line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores,
+                                        "kind": kind, "sample": sample}
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0,
+                                        "kind": "port", "sample": "failed: %s" % e}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

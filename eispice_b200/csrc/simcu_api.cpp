@@ -1,0 +1,1082 @@
+/*
+ * simcu_api.cpp - the C-ABI of libsimulator_cuda (include/simulator_cuda.h):
+ * builder calls with the reference's argument lists, device memory of one
+ * batch, and the run sequence load -> operating point -> transient kernels.
+ *
+ * There is no CPU execution path in here: every run call needs a CUDA device
+ * and fails (-1, message on stderr) without one.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "simcu_calc.h"
+#include "simcu_host.h"
+#include "simcu_kernels.h"
+
+using namespace simcu;
+
+namespace {
+
+int gQuiet = 0;
+
+int fail(const char *fmt, ...)
+{
+	if (!gQuiet) {
+		va_list ap;
+		va_start(ap, fmt);
+		std::fprintf(stderr, "simulator_cuda: ");
+		std::vfprintf(stderr, fmt, ap);
+		std::fprintf(stderr, "\n");
+		va_end(ap);
+	}
+	return -1;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return fail("%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+/* one device allocation that only ever grows */
+struct DBuf {
+	void *p = nullptr;
+	size_t bytes = 0;
+	int reserve(size_t n)
+	{
+		if (n <= bytes && p) return 0;
+		if (p) cudaFree(p);
+		p = nullptr; bytes = 0;
+		if (n == 0) n = 8;
+		cudaError_t e = cudaMalloc(&p, n);
+		if (e != cudaSuccess) {
+			p = nullptr;
+			return fail("cudaMalloc(%zu bytes): %s", n, cudaGetErrorString(e));
+		}
+		bytes = n;
+		return 0;
+	}
+	template <class T> int upload(const std::vector<T> &v, cudaStream_t st = 0)
+	{
+		if (reserve(v.size() * sizeof(T))) return -1;
+		if (v.empty()) return 0;
+		cudaError_t e = cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T),
+				cudaMemcpyHostToDevice, st);
+		return (e == cudaSuccess) ? 0 : fail("upload: %s", cudaGetErrorString(e));
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+	template <class T> T *as() const { return (T *)p; }
+};
+
+}  /* namespace */
+
+struct _simcu {
+	int M = 1;
+	Netlist nl;
+	bool locked = false;
+	/* options (reference include/control.h:34-56 + engine knobs) */
+	SimcuControl ctl;
+	double minstepOpt = -1.0;
+	int histRecordsOpt = 0, tpbOpt = 0, wsSharedOpt = -1;
+	int rawMaxPoints = 0, rawFirst = 0, rawCount = 0;
+	long long maxAttempts = 0;
+	int attemptsPerLaunch = INT_MAX;
+	double pivotThreshold = 0.1;
+	int numPilots = 8;
+	/* compiled state */
+	bool compiled = false, prepared = false, ran = false;
+	Program prog;
+	Schedule sched[2];
+	std::vector<int> forcePc[2], forcePr[2];
+	std::vector<std::string> probeNames;
+	std::vector<int> probeRows;
+	int ngrid = 0, histRecords = 0, tpb = 64, wsShared = 1;
+	SimcuArgs args[2];
+	simcuStats_ stats;
+	/* device memory */
+	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
+		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabX, dTabY, dTabM, dHistRows,
+		dProbeRows, dPmap, dPconst, dPinst, dIinst;
+	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dOutRaw, dWs, dRemaining;
+	int *hRemaining = nullptr;      /* pinned */
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+	std::vector<char *> variableNames;
+
+	_simcu()
+	{
+		std::memset(&ctl, 0, sizeof ctl);
+		ctl.itl1 = 100; ctl.itl4 = 10; ctl.maxorder = 2;          /* control.c:53-63 */
+		ctl.reltol = 0.001; ctl.vntol = 1e-6; ctl.abstol = 1e-12;
+		ctl.captol = 1e-18; ctl.chgtol = 1e-14; ctl.trtol = 1; ctl.gmin = 1e-15;
+		ctl.maxAngleA = M_PI / 3; ctl.maxAngleV = M_PI / 3;       /* :67-68 */
+		std::memset(&stats, 0, sizeof stats);
+		std::memset(args, 0, sizeof args);
+	}
+	~_simcu()
+	{
+		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
+			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabX,
+			&dTabY, &dTabM, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
+			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dOutRaw,
+			&dWs, &dRemaining};
+		for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) all[i]->release();
+		if (hRemaining) cudaFreeHost(hRemaining);
+		if (ev0) cudaEventDestroy(ev0);
+		if (ev1) cudaEventDestroy(ev1);
+		if (ev2) cudaEventDestroy(ev2);
+	}
+};
+
+/* ------------------------------------------------------------------------ *
+ * Builders.  Same argument lists, checks and row-creation order as the
+ * reference's simulatorAdd* + device*Config functions (cited per function).
+ * ------------------------------------------------------------------------ */
+namespace {
+
+bool canAdd(simcu_ *r, const char *refdes)
+{
+	if (r == nullptr || refdes == nullptr) return false;
+	if (r->locked) {      /* core/simulator.c:296 */
+		fail("Can't add a device to a simulator that has run.");
+		return false;
+	}
+	return true;
+}
+
+/* deviceNew2Pins / deviceNew4Pins: core/device.c:210-300 */
+Dev makeDev(simcu_ *r, int kind, const char *refdes, int npins, char *const pins[])
+{
+	Dev d;
+	d.kind = kind;
+	d.refdes = refdes;
+	for (int i = 0; i < npins; i++) d.pin[i] = r->nl.findOrAddRow('v', pins[i]);
+	return d;
+}
+
+/* listAdd(devices, deviceCheckDuplicate): core/device.c:166-177 */
+int commit(simcu_ *r, const Dev &d)
+{
+	if (r->nl.duplicate(d.refdes.c_str())) return fail("%s is listed twice", d.refdes.c_str());
+	r->nl.devs.push_back(d);
+	r->compiled = false; r->prepared = false;
+	return 0;
+}
+
+struct BCtx { simcu_ *r; Dev *d; };
+
+/* deviceNonlinearGetVariable: devices/nonlinear_i.c:147-192, _v.c:119-160,
+ * _c.c:127-169.  Registers the Jacobian entries of one referenced unknown. */
+int bGetVar(void *ctx, const char *name)
+{
+	BCtx *b = (BCtx *)ctx;
+	Dev &d = *b->d;
+	Netlist &nl = b->r->nl;
+	if (!std::strcmp(name, "time")) { d.usesTime = true; return CALC_VAR_TIME + 0x40000000; }
+	if (!((name[0] == 'i' || name[0] == 'v') && name[1] == '(')) {
+		fail("B element variables must be i(...), v(...) or time -- not %s", name);
+		return -1;
+	}
+	const int row = nl.findOrAddRow(0, name);
+	if (row < 0) return -1;
+	if (d.kind == DK_BI) { nl.addNode(d.pin[1], row); nl.addNode(d.rowM, row); }
+	else nl.addNode(d.rowR, row);
+	d.bvRow.push_back(row);
+	return row;
+}
+
+}  /* namespace */
+
+extern "C" {
+
+simcu_ *simcuNew(simcu_ *r, int numInstances)
+{
+	if (r != nullptr) { fail("simcuNew: argument must be NULL"); return nullptr; }
+	if (numInstances < 1) { fail("simcuNew: numInstances must be >= 1"); return nullptr; }
+	simcu_ *s = new _simcu();
+	s->M = numInstances;
+	return s;
+}
+
+int simcuDestroy(simcu_ **r)
+{
+	if (r == nullptr || *r == nullptr) return -1;
+	for (size_t i = 0; i < (*r)->variableNames.size(); i++) std::free((*r)->variableNames[i]);
+	delete *r;
+	*r = nullptr;
+	return 0;
+}
+
+int simcuInfo(void)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	std::printf("simulator_cuda %d.%d: %d CUDA device(s)%s\n", SIMCU_MAJOR_VERSION,
+			SIMCU_MINOR_VERSION, (e == cudaSuccess) ? n : 0,
+			(e == cudaSuccess) ? "" : " (no driver)");
+	return 0;
+}
+
+int simcuSetDevice(int device)
+{
+	CU(cudaSetDevice(device));
+	return 0;
+}
+
+void simcuFree(void *p) { std::free(p); }
+
+/* simulatorAddResistor: core/simulator.c:288-309, devices/resistor.c:111-144 */
+int simcuAddResistor(simcu_ *r, char *refdes, char *pNode, char *nNode, double *resistance)
+{
+	if (!canAdd(r, refdes) || !pNode || !nNode || !resistance) return -1;
+	char *pins[2] = {pNode, nNode};
+	Dev d = makeDev(r, DK_R, refdes, 2, pins);
+	d.val = resistance;
+	const int K = d.pin[0], J = d.pin[1];
+	r->nl.addNode(K, K); r->nl.addNode(K, J); r->nl.addNode(J, K); r->nl.addNode(J, J);
+	return commit(r, d);
+}
+
+/* simulatorAddCapacitor: core/simulator.c:313-334, devices/capacitor.c:216-260 */
+int simcuAddCapacitor(simcu_ *r, char *refdes, char *pNode, char *nNode, double *capacitance)
+{
+	if (!canAdd(r, refdes) || !pNode || !nNode || !capacitance) return -1;
+	char *pins[2] = {pNode, nNode};
+	Dev d = makeDev(r, DK_C, refdes, 2, pins);
+	d.val = capacitance;
+	const int K = d.pin[0], J = d.pin[1];
+	r->nl.addNode(K, K); r->nl.addNode(J, K); r->nl.addNode(K, J); r->nl.addNode(J, J);
+	return commit(r, d);
+}
+
+/* simulatorAddInductor: core/simulator.c:338-359, devices/inductor.c:222-269 */
+int simcuAddInductor(simcu_ *r, char *refdes, char *pNode, char *nNode, double *inductance)
+{
+	if (!canAdd(r, refdes) || !pNode || !nNode || !inductance) return -1;
+	char *pins[2] = {pNode, nNode};
+	Dev d = makeDev(r, DK_L, refdes, 2, pins);
+	d.val = inductance;
+	d.rowR = r->nl.findOrAddRow('i', refdes);
+	const int K = d.pin[0], J = d.pin[1], R = d.rowR;
+	r->nl.addNode(R, K); r->nl.addNode(R, J); r->nl.addNode(K, R); r->nl.addNode(J, R);
+	r->nl.addNode(R, R);
+	return commit(r, d);
+}
+
+/* simulatorAddSource: core/simulator.c:430-457, devices/source_v.c:202-252,
+ * source_i.c:195-238, math/waveform.c:95-168 */
+int simcuAddSource(simcu_ *r, char *refdes, char *pNode, char *nNode, char type,
+		double *dc, char stimulus, double *args[7])
+{
+	if (!canAdd(r, refdes) || !pNode || !nNode) return -1;
+	type = (char)std::tolower((unsigned char)type);
+	if (type != 'v' && type != 'i') return fail("Source type must be either i or v, not %c", type);
+	char *pins[2] = {pNode, nNode};
+	Dev d = makeDev(r, (type == 'v') ? DK_V : DK_I, refdes, 2, pins);
+	if (type == 'v' && d.pin[0] == 0 && d.pin[1] == 0)
+		return fail("Source %s has both nodes shorted to 0!", refdes);
+	d.val = dc;
+	d.wtype = stimulus;
+	if (stimulus != 0) {
+		if (!std::strchr("pgselcf", stimulus)) return fail("Unsupported waveform type %c", stimulus);
+		if (args == nullptr) return fail("Source %s: waveform arguments missing", refdes);
+		static const struct { char t; int n; } used[] = {
+			{'p', 7}, {'g', 7}, {'s', 5}, {'e', 6}, {'l', 2}, {'c', 2}, {'f', 5}};
+		int n = 0;
+		for (size_t i = 0; i < sizeof used / sizeof used[0]; i++) if (used[i].t == stimulus) n = used[i].n;
+		for (int i = 0; i < n; i++)
+			if (args[i] == nullptr) return fail("Argument %i is NULL", i);
+		if (stimulus == 'l' || stimulus == 'c') {
+			d.wtab = (double **)args[0];
+			d.wtabLen = (int *)args[1];
+		} else {
+			for (int i = 0; i < n; i++) d.wargs[i] = args[i];
+		}
+	} else if (dc == nullptr) {
+		return fail("Source %s needs a DC value", refdes);
+	}
+	if (type == 'v') {
+		d.rowR = r->nl.findOrAddRow('i', refdes);
+		const int K = d.pin[0], J = d.pin[1], R = d.rowR;
+		r->nl.addNode(R, K); r->nl.addNode(R, J); r->nl.addNode(K, R); r->nl.addNode(J, R);
+	}
+	return commit(r, d);
+}
+
+/* simulatorAddTLine: core/simulator.c:461-487, devices/tline.c:353-457 */
+int simcuAddTLine(simcu_ *r, char *refdes, char *pNodeLeft, char *nNodeLeft,
+		char *pNodeRight, char *nNodeRight, double *Z0, double *Td, double *loss)
+{
+	if (!canAdd(r, refdes) || !pNodeLeft || !nNodeLeft || !pNodeRight || !nNodeRight ||
+			!Z0 || !Td) return -1;
+	char *pins[4] = {pNodeLeft, nNodeLeft, pNodeRight, nNodeRight};
+	Dev d = makeDev(r, DK_T, refdes, 4, pins);
+	if (d.pin[0] == 0 && d.pin[1] == 0)
+		return fail("T-Line %s has both input nodes shorted to 0!", refdes);
+	if (d.pin[2] == 0 && d.pin[3] == 0)
+		return fail("T-Line %s has both output nodes shorted to 0!", refdes);
+	d.z0 = Z0; d.td = Td; d.loss = loss;
+	d.rowR = r->nl.findOrAddRow('i', (std::string(refdes) + "#in1").c_str());
+	d.rowM = r->nl.findOrAddRow('i', (std::string(refdes) + "#in2").c_str());
+	const int K = d.pin[0], J = d.pin[1], L = d.pin[2], M = d.pin[3], R = d.rowR, S = d.rowM;
+	const int rc[18][2] = {{R, K}, {R, J}, {K, R}, {J, R}, {R, L}, {R, M}, {S, L}, {S, M},
+		{L, S}, {M, S}, {S, K}, {S, J}, {R, R}, {S, S}, {K, S}, {J, S}, {L, R}, {M, R}};
+	for (int i = 0; i < 18; i++) r->nl.addNode(rc[i][0], rc[i][1]);
+	return commit(r, d);
+}
+
+/* simulatorAddVICurve: core/simulator.c:512-538, devices/vicurve.c:298-359 */
+int simcuAddVICurve(simcu_ *r, char *refdes, char *pNode, char *nNode, double **vi,
+		int *viLength, char viType, double **ta, int *taLength, char taType)
+{
+	if (!canAdd(r, refdes) || !pNode || !nNode) return -1;
+	if (!vi || !*vi || !viLength || *viLength < 1) return fail("VI curve %s needs a table", refdes);
+	if (viType != 'l' && viType != 'c') return fail("VI table type must be l or c");
+	char *pins[2] = {pNode, nNode};
+	Dev d = makeDev(r, DK_VI, refdes, 2, pins);
+	TableSet s; s.vi = vi; s.viLen = viLength; s.ta = ta; s.taLen = taLength;
+	d.sets.push_back(s);
+	d.viType = viType;
+	d.taType = (taType == 'c') ? 'c' : 'l';
+	d.rowR = r->nl.findOrAddRow('i', refdes);
+	d.rowM = r->nl.findOrAddRow('v', refdes);
+	const int K = d.pin[0], J = d.pin[1], R = d.rowR, M = d.rowM;
+	r->nl.addNode(R, K); r->nl.addNode(R, M); r->nl.addNode(K, R); r->nl.addNode(M, R);
+	r->nl.addNode(J, J); r->nl.addNode(J, M); r->nl.addNode(M, J); r->nl.addNode(M, M);
+	return commit(r, d);
+}
+
+/* simulatorAddNonlinearSource: core/simulator.c:363-392, devices/
+ * nonlinear_i.c:368-425, nonlinear_v.c:330-392, nonlinear_c.c:429-495.  The
+ * reference tokenises the equation here and parses it at every evaluation; a
+ * syntax error therefore surfaces at the first run there and already here. */
+int simcuAddNonlinearSource(simcu_ *r, char *refdes, char *pNode, char *nNode, char type,
+		char *equation)
+{
+	if (!canAdd(r, refdes) || !pNode || !nNode || !equation) return -1;
+	type = (char)std::tolower((unsigned char)type);
+	if (type != 'i' && type != 'v' && type != 'c')
+		return fail("Nonlinear Source type must be either i, v or c, not %c", type);
+	char *pins[2] = {pNode, nNode};
+	Dev d = makeDev(r, (type == 'i') ? DK_BI : (type == 'v') ? DK_BV : DK_BC, refdes, 2, pins);
+	const int K = d.pin[0], J = d.pin[1];
+	Netlist &nl = r->nl;
+	if (type == 'i') {
+		d.rowR = nl.findOrAddRow('i', refdes);
+		d.rowM = nl.findOrAddRow('v', refdes);
+		nl.addNode(d.rowR, K); nl.addNode(d.rowR, d.rowM);
+		nl.addNode(K, d.rowR); nl.addNode(d.rowM, d.rowR);
+	} else if (type == 'v') {
+		if (K == 0 && J == 0) return fail("Source %s has both input nodes shorted to 0!", refdes);
+		d.rowR = nl.findOrAddRow('i', refdes);
+		nl.addNode(d.rowR, K); nl.addNode(d.rowR, J);
+		nl.addNode(K, d.rowR); nl.addNode(J, d.rowR);
+	} else {
+		nl.addNode(K, K); nl.addNode(J, K); nl.addNode(K, J); nl.addNode(J, J);
+		d.rowR = nl.findOrAddRow('i', refdes);
+		d.rowM = nl.findOrAddRow('v', refdes);
+		nl.addNode(d.rowR, d.rowM); nl.addNode(d.rowM, d.rowR);
+	}
+	BCtx ctx; ctx.r = r; ctx.d = &d;
+	std::string err;
+	if (!calcCompile(equation, bGetVar, &ctx, d.calc, err))
+		return fail("Bad B equation for %s (%s): %s", refdes, err.c_str(), equation);
+	/* calc variable index of each Jacobian variable; "time" has no Jacobian */
+	for (size_t i = 0; i < d.calc.varRef.size(); i++) {
+		if (d.calc.varRef[i] == CALC_VAR_TIME + 0x40000000) d.calc.varRef[i] = CALC_VAR_TIME;
+		else d.bvCalcVar.push_back((int)i);
+	}
+	return commit(r, d);
+}
+
+int simcuAddCallbackSource(simcu_ *, char *refdes, char *, char *, char, char *[], double[],
+		double[], int, void *, void *)
+{
+	return fail("%s: callback (PyB) sources call back into the interpreter at every Newton "
+			"iteration and cannot be batched", refdes ? refdes : "?");
+}
+
+int simcuAddTLineW(simcu_ *, char *refdes, char *[], int, int *, double *, double **, double **,
+		double **, double **, double **, double **, double *, double *)
+{
+	return fail("%s: the W-element is unfinished in the reference and not supported",
+			refdes ? refdes : "?");
+}
+
+/* ---- the instance dimension ------------------------------------------------ */
+int simcuSetInstanceParam(simcu_ *r, char *refdes, char *name, const double *values, int stride)
+{
+	if (!r || !refdes || !name || !values) return -1;
+	Dev *d = r->nl.find(refdes);
+	if (!d) return fail("unknown device %s", refdes);
+	bool ok = false;
+	const std::string n(name);
+	switch (d->kind) {
+	case DK_R: ok = (n == "R"); break;
+	case DK_C: ok = (n == "C"); break;
+	case DK_L: ok = (n == "L"); break;
+	case DK_T: ok = (n == "Z0" || n == "Td" || n == "loss"); break;
+	case DK_V: case DK_I:
+		ok = (n == "DC") || (n.size() == 2 && n[0] == 'A' && n[1] >= '0' && n[1] <= '6' &&
+				d->wtype && d->wtype != 'l' && d->wtype != 'c');
+		break;
+	default: break;
+	}
+	if (!ok) return fail("unknown parameter %s.%s", refdes, name);
+	const bool isNew = !d->inst.count(n);
+	std::vector<double> &v = d->inst[n];
+	v.resize(r->M);
+	for (int i = 0; i < r->M; i++) v[i] = values[(size_t)i * stride];
+	if (isNew) { r->compiled = false; r->prepared = false; }
+	return 0;
+}
+
+int simcuAddVITableSet(simcu_ *r, char *refdes, double **vi, int *viLength, double **ta,
+		int *taLength)
+{
+	if (!r || !refdes) return -1;
+	if (r->locked) return fail("Can't add a table set to a simulator that has run.");
+	Dev *d = r->nl.find(refdes);
+	if (!d || d->kind != DK_VI) return fail("%s is not a VI device", refdes);
+	if (!vi || !*vi || !viLength || *viLength < 1) return fail("VI curve %s needs a table", refdes);
+	TableSet s; s.vi = vi; s.viLen = viLength; s.ta = ta; s.taLen = taLength;
+	d->sets.push_back(s);
+	r->compiled = false; r->prepared = false;
+	return (int)d->sets.size() - 1;
+}
+
+int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex, int stride)
+{
+	if (!r || !refdes || !setIndex) return -1;
+	Dev *d = r->nl.find(refdes);
+	if (!d || d->kind != DK_VI) return fail("%s is not a VI device", refdes);
+	const bool isNew = d->instSet.empty();
+	d->instSet.resize(r->M);
+	for (int i = 0; i < r->M; i++) d->instSet[i] = setIndex[(size_t)i * stride];
+	if (isNew) { r->compiled = false; r->prepared = false; }
+	return 0;
+}
+
+int simcuSetOption(simcu_ *r, char *name, double value)
+{
+	if (!name) return -1;
+	const std::string n(name);
+	if (n == "quiet") { gQuiet = (value != 0.0); return 0; }
+	if (!r) return -1;
+	SimcuControl &c = r->ctl;
+	if (n == "reltol") c.reltol = value; else if (n == "vntol") c.vntol = value;
+	else if (n == "abstol") c.abstol = value; else if (n == "captol") c.captol = value;
+	else if (n == "chgtol") c.chgtol = value; else if (n == "trtol") c.trtol = value;
+	else if (n == "gmin") c.gmin = value; else if (n == "itl1") c.itl1 = (int)value;
+	else if (n == "itl4") c.itl4 = (int)value; else if (n == "maxorder") c.maxorder = (int)value;
+	else if (n == "minstep") r->minstepOpt = value;
+	else if (n == "hist_records") r->histRecordsOpt = (int)value;
+	else if (n == "max_attempts") r->maxAttempts = (long long)value;
+	else if (n == "attempts_per_launch") r->attemptsPerLaunch = (value < 1) ? INT_MAX : (int)value;
+	else if (n == "threads_per_block") r->tpbOpt = (int)value;
+	else if (n == "workspace_shared") r->wsSharedOpt = (int)value;
+	else if (n == "raw_max_points") r->rawMaxPoints = (int)value;
+	else if (n == "raw_first") r->rawFirst = (int)value;
+	else if (n == "raw_count") r->rawCount = (int)value;
+	else if (n == "pivot_threshold") { r->pivotThreshold = value; r->sched[0].lu.clear(); r->sched[1].lu.clear(); }
+	else if (n == "num_pilots") r->numPilots = std::max(1, (int)value);
+	else return fail("unknown option %s", name);
+	r->prepared = false;
+	return 0;
+}
+
+int simcuSetPivots(simcu_ *r, int phase, const int *pc, const int *pr, int n)
+{
+	if (!r || phase < 0 || phase > 1) return -1;
+	r->forcePc[phase].clear(); r->forcePr[phase].clear();
+	if (pc && pr) {
+		r->forcePc[phase].assign(pc, pc + n);
+		r->forcePr[phase].assign(pr, pr + n);
+	}
+	r->prepared = false;
+	return 0;
+}
+
+}  /* extern "C" */
+
+/* ------------------------------------------------------------------------ *
+ * Preparation: compile, upload, allocate, symbolic analysis on pilots
+ * ------------------------------------------------------------------------ */
+namespace {
+
+int ensureCompiled(simcu_ *r)
+{
+	std::string err;
+	if (!r->compiled) {
+		if (!compileProgram(r->nl, r->M, r->prog, err)) return fail("%s", err.c_str());
+		r->compiled = true;
+		r->sched[0] = Schedule(); r->sched[1] = Schedule();
+	} else if (!refreshParameters(r->nl, r->M, r->prog, err)) {
+		return fail("%s", err.c_str());
+	}
+	return 0;
+}
+
+int uploadParameters(simcu_ *r, cudaStream_t st)
+{
+	const Program &p = r->prog;
+	if (r->dPmap.upload(p.pmap, st) || r->dPconst.upload(p.pconst, st) ||
+			r->dPinst.upload(p.pinst, st) || r->dIinst.upload(p.iinst, st) ||
+			r->dTabOff.upload(p.tabOff, st) || r->dTabType.upload(p.tabType, st) ||
+			r->dTabX.upload(p.tabX, st) || r->dTabY.upload(p.tabY, st) ||
+			r->dTabM.upload(p.tabM, st))
+		return -1;
+	for (int ph = 0; ph < 2; ph++) {
+		SimcuArgs &a = r->args[ph];
+		a.pmap = r->dPmap.as<int>(); a.pconst = r->dPconst.as<double>();
+		a.pinst = r->dPinst.as<double>(); a.iinst = r->dIinst.as<int>();
+		a.tabOff = r->dTabOff.as<int>(); a.tabType = r->dTabType.as<int>();
+		a.tabX = r->dTabX.as<double>(); a.tabY = r->dTabY.as<double>();
+		a.tabM = r->dTabM.as<double>();
+	}
+	return 0;
+}
+
+int uploadSchedule(simcu_ *r, int ph)
+{
+	const Schedule &s = r->sched[ph];
+	if (r->dLu[ph].upload(s.lu) || r->dXslot[ph].upload(s.xslot)) return -1;
+	SimcuArgs &a = r->args[ph];
+	a.lu = r->dLu[ph].as<int>(); a.luLen = (int)s.lu.size();
+	a.xslot = r->dXslot[ph].as<int>();
+	a.F = s.F;
+	return 0;
+}
+
+/* threads per block and where the LU workspace lives */
+int chooseLaunchShape(simcu_ *r)
+{
+	const int words = std::max(r->sched[0].F, r->sched[1].F) + r->prog.N;
+	int dev = 0, maxSmem = 0;
+	CU(cudaGetDevice(&dev));
+	CU(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+	int tpb = r->tpbOpt > 0 ? r->tpbOpt : 64;
+	tpb = std::max(32, (tpb / 32) * 32);
+	int shared = (r->wsSharedOpt < 0) ? 1 : r->wsSharedOpt;
+	if (shared) {
+		while (tpb > 32 && (size_t)words * tpb * 8 > (size_t)maxSmem) tpb -= 32;
+		if ((size_t)words * tpb * 8 > (size_t)maxSmem) {
+			if (r->wsSharedOpt == 1) return fail("LU workspace does not fit shared memory");
+			shared = 0;
+			tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 128;
+		}
+	}
+	r->tpb = tpb; r->wsShared = shared;
+	if (!shared && r->dWs.reserve((size_t)words * r->M * 8)) return -1;
+	for (int ph = 0; ph < 2; ph++) {
+		r->args[ph].wsShared = shared;
+		r->args[ph].wsGlobal = r->dWs.as<double>();
+	}
+	return 0;
+}
+
+int downloadPilots(simcu_ *r, std::vector<std::vector<double> > &pilots)
+{
+	const int M = r->M, nnz = r->prog.nnzA;
+	const int P = std::min(M, r->numPilots);
+	pilots.assign(P, std::vector<double>(nnz));
+	for (int q = 0; q < P; q++) {
+		const int i = (P > 1) ? (int)((long long)q * (M - 1) / (P - 1)) : 0;
+		CU(cudaMemcpy2D(pilots[q].data(), sizeof(double), r->dA.as<double>() + i,
+				(size_t)M * sizeof(double), sizeof(double), nnz, cudaMemcpyDeviceToHost));
+	}
+	return 0;
+}
+
+int analysePhase(simcu_ *r, int ph)
+{
+	std::vector<std::vector<double> > pilots;
+	if (downloadPilots(r, pilots)) return -1;
+	std::string err;
+	const Program &p = r->prog;
+	const bool forced = !r->forcePc[ph].empty();
+	if (forced && (int)r->forcePc[ph].size() != p.N) return fail("forced pivot sequence has the wrong length");
+	/* a slot the flattener believes is exactly zero in this phase must be */
+	std::vector<char> active = ph ? p.activeTran : p.activeOP;
+	for (size_t q = 0; q < pilots.size(); q++)
+		for (int s = 0; s < p.nnzA; s++)
+			if (!active[s] && pilots[q][s] != 0.0) active[s] = 1;
+	if (!analyse(p.N, p.colStart, p.rowIdx, active, pilots,
+			r->pivotThreshold, forced ? r->forcePc[ph].data() : nullptr,
+			forced ? r->forcePr[ph].data() : nullptr, r->sched[ph], err))
+		return fail("%s analysis: %s", ph ? "transient" : "operating-point", err.c_str());
+	return uploadSchedule(r, ph);
+}
+
+int resetState(simcu_ *r, cudaStream_t st)
+{
+	const Program &p = r->prog;
+	CU(cudaMemsetAsync(r->dS.p, 0, (size_t)std::max(1, p.stateDoubles) * r->M * 8, st));
+	CU(cudaMemsetAsync(r->dIS.p, 0, (size_t)std::max(1, p.stateInts) * r->M * 4, st));
+	return 0;
+}
+
+int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], int numProbes,
+		bool opOnly)
+{
+	if (!r) return -1;
+	if (r->nl.devs.empty()) return fail("empty circuit");
+	int ndevice = 0;
+	if (cudaGetDeviceCount(&ndevice) != cudaSuccess || ndevice < 1)
+		return fail("no CUDA device: the batched engine has no CPU path");
+	if (ensureCompiled(r)) return -1;
+	r->locked = true;
+	const Program &p = r->prog;
+	const int M = r->M;
+
+	/* run constants: core/simulator.c:91-109 */
+	SimcuControl c = r->ctl;
+	if (opOnly) { tstep = 1.0; tstop = 0.0; tmax = 1.0; }
+	else {
+		if (!(tstep > 0.0) || !(tstop > 0.0)) return fail("tstep and tstop must be positive");
+		if (tmax == 0.0) { tmax = tstop / 50; tmax = (tstep < tmax) ? tstep : tmax; }
+	}
+	c.tstep = tstep; c.tstop = tstop; c.tmax = tmax;
+	c.minstep = (r->minstepOpt < 0) ? tstep * 5e-5 : r->minstepOpt;
+	const bool runChanged = !r->prepared || c.tstep != r->ctl.tstep || c.tstop != r->ctl.tstop ||
+		c.tmax != r->ctl.tmax;
+	r->ctl = c;
+
+	/* probes and output grid */
+	r->probeNames.clear(); r->probeRows.clear();
+	for (int i = 0; i < numProbes; i++) {
+		const int row = r->nl.findRow(probes[i]);
+		if (row < 1) return fail("unknown probe %s", probes[i] ? probes[i] : "(null)");
+		r->probeNames.push_back(probes[i]);
+		r->probeRows.push_back(row);
+	}
+	r->ngrid = 0;
+	if (!opOnly && numProbes > 0) {
+		int ng = (int)std::floor(tstop / tstep * (1.0 + 1e-12)) + 1;
+		if ((ng - 1) * tstep < tstop * (1.0 - 1e-9)) ng++;
+		r->ngrid = ng;
+	}
+
+	/* program upload */
+	if (r->dDev.upload(p.dev) || r->dBvar.upload(p.bvar) || r->dCalcOff.upload(p.calcOff) ||
+			r->dCalcCode.upload(p.calcCode) || r->dCalcConst.upload(p.calcConst) ||
+			r->dCalcVarOff.upload(p.calcVarOff) || r->dCalcVars.upload(p.calcVars) ||
+			r->dHistRows.upload(p.histRows) || r->dProbeRows.upload(r->probeRows))
+		return -1;
+
+	/* T-line history ring length */
+	const int nh = (int)p.histRows.size();
+	int R = 0;
+	if (nh > 0 && !opOnly) {
+		R = r->histRecordsOpt;
+		if (R <= 0) {
+			size_t freeB = 0, totalB = 0;
+			CU(cudaMemGetInfo(&freeB, &totalB));
+			const double per = (double)(nh + 1) * 8.0 * M;
+			R = (int)std::min(4096.0, std::max(64.0, 0.25 * (double)totalB / per));
+		}
+	}
+	r->histRecords = R;
+
+	/* per-instance state */
+	const size_t m8 = (size_t)M * 8, m4 = (size_t)M * 4;
+	if (r->dA.reserve(p.nnzA * m8) || r->dB.reserve(p.N * m8) || r->dX.reserve(p.N * m8) ||
+			r->dS.reserve(std::max(1, p.stateDoubles) * m8) ||
+			r->dIS.reserve(std::max(1, p.stateInts) * m4) ||
+			r->dCD.reserve(CD_NUM * m8) || r->dCI.reserve(CI_NUM * m4) ||
+			r->dHt.reserve((size_t)R * m8) || r->dHx.reserve((size_t)R * nh * m8) ||
+			r->dOutGrid.reserve((size_t)r->ngrid * numProbes * m8) ||
+			r->dRemaining.reserve(sizeof(int)))
+		return -1;
+	if (r->rawMaxPoints > 0) {
+		if (r->rawCount < 1) { r->rawFirst = 0; r->rawCount = M; }
+		if (r->rawFirst < 0 || r->rawFirst + r->rawCount > M) return fail("raw_first/raw_count out of range");
+		if (r->dOutRaw.reserve((size_t)r->rawMaxPoints * (p.N + 1) * r->rawCount * 8)) return -1;
+	}
+	if (!r->hRemaining) CU(cudaMallocHost((void **)&r->hRemaining, sizeof(int)));
+	if (!r->ev0) {
+		CU(cudaEventCreate(&r->ev0)); CU(cudaEventCreate(&r->ev1)); CU(cudaEventCreate(&r->ev2));
+	}
+
+	for (int ph = 0; ph < 2; ph++) {
+		SimcuArgs &a = r->args[ph];
+		a.M = M; a.N = p.N; a.nnzA = p.nnzA; a.ndev = p.ndev; a.ctl = r->ctl;
+		a.dev = r->dDev.as<int>(); a.bvar = r->dBvar.as<int>();
+		a.calcOff = r->dCalcOff.as<int>(); a.calcCode = r->dCalcCode.as<int>();
+		a.calcConst = r->dCalcConst.as<double>();
+		a.calcVarOff = r->dCalcVarOff.as<int>(); a.calcVars = r->dCalcVars.as<int>();
+		a.histRows = r->dHistRows.as<int>(); a.nh = nh; a.histRecords = R;
+		a.probeRows = r->dProbeRows.as<int>(); a.nprobes = numProbes; a.ngrid = r->ngrid;
+		a.rawMaxPoints = r->rawMaxPoints; a.rawFirst = r->rawFirst; a.rawCount = r->rawCount;
+		a.A = r->dA.as<double>(); a.B = r->dB.as<double>(); a.X = r->dX.as<double>();
+		a.Xrec = nullptr; a.S = r->dS.as<double>(); a.CD = r->dCD.as<double>();
+		a.IS = r->dIS.as<int>(); a.CI = r->dCI.as<int>();
+		a.Ht = r->dHt.as<double>(); a.Hx = r->dHx.as<double>();
+		a.outGrid = r->dOutGrid.as<double>(); a.outRaw = r->dOutRaw.as<double>();
+		a.attemptsPerLaunch = r->attemptsPerLaunch;
+		a.maxAttempts = (r->maxAttempts > 0) ? r->maxAttempts : LLONG_MAX;
+		a.remaining = r->dRemaining.as<int>();
+		a.stopBeforeSolve = 0;
+	}
+	if (uploadParameters(r, 0)) return -1;
+
+	/* symbolic analysis on a pilot pass (one-off per topology and time scale) */
+	const bool needOP = r->sched[0].lu.empty() || !r->forcePc[0].empty();
+	const bool needTran = !opOnly && (r->sched[1].lu.empty() || runChanged || !r->forcePc[1].empty());
+	if (needOP || needTran) {
+		r->args[0].wsShared = 0; r->args[1].wsShared = 0;
+		if (resetState(r, 0)) return -1;
+		if (simcuLaunchLoad(&r->args[0], 64, 0)) return fail("load kernel launch failed");
+		if (needOP && analysePhase(r, 0)) return -1;
+		if (needTran) {
+			if (r->sched[1].lu.empty()) r->sched[1].F = p.nnzA;
+			if (chooseLaunchShape(r)) return -1;
+			if (simcuLaunchOp(&r->args[0], r->tpb, 0, 0)) return fail("op kernel launch failed");
+			SimcuArgs pilot = r->args[1];
+			pilot.stopBeforeSolve = 1; pilot.attemptsPerLaunch = 1;
+			pilot.F = 0; pilot.rawMaxPoints = 0; pilot.nprobes = 0;
+			if (simcuLaunchTran(&pilot, r->tpb, 0)) return fail("tran kernel launch failed");
+			CU(cudaDeviceSynchronize());
+			if (analysePhase(r, 1)) return -1;
+		}
+	}
+	if (opOnly && r->sched[1].lu.empty()) r->sched[1].F = r->sched[0].F;
+	if (chooseLaunchShape(r)) return -1;
+	CU(cudaDeviceSynchronize());
+	r->prepared = true;
+	return 0;
+}
+
+int runDevice(simcu_ *r, cudaStream_t st, bool opOnly)
+{
+	if (!r || !r->prepared) return fail("simcuRunDevice before simcuPrepare");
+	int launches = 0;
+	CU(cudaEventRecord(r->ev0, st));
+	if (resetState(r, st)) return -1;
+	if (simcuLaunchLoad(&r->args[0], 128, st)) return fail("load kernel launch failed");
+	if (simcuLaunchOp(&r->args[0], r->tpb, opOnly ? 1 : 0, st)) return fail("op kernel launch failed");
+	launches += 2;
+	CU(cudaEventRecord(r->ev2, st));
+	while (!opOnly) {
+		CU(cudaMemsetAsync(r->dRemaining.p, 0, sizeof(int), st));
+		if (simcuLaunchTran(&r->args[1], r->tpb, st)) return fail("tran kernel launch failed");
+		launches++;
+		CU(cudaMemcpyAsync(r->hRemaining, r->dRemaining.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		if (*r->hRemaining <= 0) break;
+	}
+	CU(cudaEventRecord(r->ev1, st));
+	CU(cudaStreamSynchronize(st));
+	float ms = 0.f;
+	CU(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
+	r->stats.kernelLaunches = launches;
+	r->stats.deviceMs = ms;
+	CU(cudaEventElapsedTime(&ms, r->ev2, r->ev1));
+	r->stats.tranMs = ms;
+	r->ran = true;
+	return 0;
+}
+
+int collectStats(simcu_ *r)
+{
+	const int M = r->M;
+	std::vector<int> ci((size_t)CI_NUM * M);
+	CU(cudaMemcpy(ci.data(), r->dCI.p, ci.size() * sizeof(int), cudaMemcpyDeviceToHost));
+	simcuStats_ &s = r->stats;
+	s.accepted = s.rejectedLTE = s.rejectedNC = s.factorizations = s.opFactorizations = s.failed = 0;
+	for (int i = 0; i < M; i++) {
+		s.accepted += ci[(size_t)CI_ACCEPTED * M + i];
+		s.rejectedLTE += ci[(size_t)CI_REJ_LTE * M + i];
+		s.rejectedNC += ci[(size_t)CI_REJ_NC * M + i];
+		s.factorizations += ci[(size_t)CI_NFACT * M + i];
+		s.opFactorizations += ci[(size_t)CI_NFACT_OP * M + i];
+		s.failed += (ci[(size_t)CI_STATUS * M + i] != 0);
+	}
+	const Program &p = r->prog;
+	s.numUnknowns = p.N; s.numNonzeros = p.nnzA;
+	s.numFactor = r->sched[1].nL + r->sched[1].nU + p.N;
+	s.numFactorOP = r->sched[0].nL + r->sched[0].nU + p.N;
+	s.stateDoubles = p.stateDoubles;
+	s.histRows = (int)p.histRows.size(); s.histRecords = r->histRecords;
+	s.workspaceInShared = r->wsShared; s.threadsPerBlock = r->tpb;
+	return 0;
+}
+
+/* raw (time, X) record of one instance as the reference lays it out:
+ * core/matrix.c:430-470, [numPoints][numVariables], column 0 = time */
+int fetchRaw(simcu_ *r, int instance, double **data, int *numPoints)
+{
+	if (r->rawMaxPoints <= 0 || instance < r->rawFirst || instance >= r->rawFirst + r->rawCount)
+		return fail("instance %d was not recorded", instance);
+	const int nv = r->prog.N + 1;
+	int npts = 0;
+	CU(cudaMemcpy(&npts, r->dCI.as<int>() + (size_t)CI_NPTS * r->M + instance, sizeof(int),
+			cudaMemcpyDeviceToHost));
+	*numPoints = npts;
+	if (npts > r->rawMaxPoints) return 1;       /* caller enlarges and reruns */
+	double *out = (double *)std::malloc(sizeof(double) * (size_t)std::max(1, npts) * nv);
+	if (!out) return fail("out of memory");
+	if (npts > 0)
+		CU(cudaMemcpy2D(out, sizeof(double),
+				r->dOutRaw.as<double>() + (instance - r->rawFirst),
+				(size_t)r->rawCount * sizeof(double), sizeof(double), (size_t)npts * nv,
+				cudaMemcpyDeviceToHost));
+	*data = out;
+	return 0;
+}
+
+int variablesOf(simcu_ *r, char ***variables, int *numVariables)
+{
+	const int nv = r->prog.N + 1;
+	if (r->variableNames.empty()) {
+		r->variableNames.push_back(strdup("time"));
+		for (int k = 1; k <= r->prog.N; k++) r->variableNames.push_back(strdup(r->nl.rowName[k].c_str()));
+	}
+	if (numVariables) *numVariables = nv;
+	if (variables) {
+		char **v = (char **)std::malloc(sizeof(char *) * (nv + 1));
+		if (!v) return fail("out of memory");
+		for (int k = 0; k < nv; k++) v[k] = r->variableNames[k];
+		v[nv] = nullptr;
+		*variables = v;
+	}
+	return 0;
+}
+
+int runSingle(simcu_ *r, bool opOnly, double tstep, double tstop, double tmax, int instance,
+		double *data[], char **variables[], int *numPoints, int *numVariables)
+{
+	if (!r || !data || !numPoints) return -1;
+	if (instance < 0 || instance >= r->M) return fail("instance out of range");
+	const int saveMax = r->rawMaxPoints, saveFirst = r->rawFirst, saveCount = r->rawCount;
+	int cap = opOnly ? 4 : 8192;
+	int rc = -1;
+	for (int attempt = 0; attempt < 2; attempt++) {
+		r->rawMaxPoints = cap; r->rawFirst = instance; r->rawCount = 1;
+		r->prepared = false;
+		if (prepare(r, tstep, tstop, tmax, nullptr, 0, opOnly)) break;
+		if (runDevice(r, 0, opOnly)) break;
+		int status = 0;
+		if (cudaMemcpy(&status, r->dCI.as<int>() + (size_t)CI_STATUS * r->M + instance,
+				sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+		if (status != 0) {
+			static const char *const why[] = {"", "Timestep too small", "U is singular",
+				"NaN in a device evaluation", "operating point failed to converge",
+				"T-line history ring too short", "attempt budget exhausted"};
+			fail("%s", why[(status >= 0 && status <= 6) ? status : 0]);
+			break;
+		}
+		rc = fetchRaw(r, instance, data, numPoints);
+		if (rc != 1) break;
+		cap = *numPoints + 16;
+		rc = -1;
+	}
+	r->rawMaxPoints = saveMax; r->rawFirst = saveFirst; r->rawCount = saveCount;
+	r->prepared = false;
+	if (rc != 0) return -1;
+	collectStats(r);
+	return variablesOf(r, variables, numVariables);
+}
+
+}  /* namespace */
+
+extern "C" {
+
+int simcuPrepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], int numProbes)
+{
+	return prepare(r, tstep, tstop, tmax, probes, numProbes, false);
+}
+
+int simcuUpload(simcu_ *r, void *stream)
+{
+	if (!r || !r->prepared) return fail("simcuUpload before simcuPrepare");
+	std::string err;
+	if (!refreshParameters(r->nl, r->M, r->prog, err)) return fail("%s", err.c_str());
+	return uploadParameters(r, (cudaStream_t)stream);
+}
+
+int simcuRunDevice(simcu_ *r, void *stream) { return runDevice(r, (cudaStream_t)stream, false); }
+
+int simcuFetch(simcu_ *r, double *data, int *status, void *stream)
+{
+	if (!r || !r->ran) return fail("simcuFetch before simcuRunDevice");
+	cudaStream_t st = (cudaStream_t)stream;
+	const int M = r->M, rows = r->ngrid * (int)r->probeRows.size();
+	if (data && rows > 0) {
+		if (r->dOutT.reserve((size_t)rows * M * 8)) return -1;
+		if (simcuLaunchTranspose(r->dOutGrid.as<double>(), r->dOutT.as<double>(), M, rows, st))
+			return fail("transpose kernel launch failed");
+		CU(cudaMemcpyAsync(data, r->dOutT.p, (size_t)rows * M * 8, cudaMemcpyDeviceToHost, st));
+	}
+	if (status)
+		CU(cudaMemcpyAsync(status, r->dCI.as<int>() + (size_t)CI_STATUS * M, (size_t)M * 4,
+				cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return 0;
+}
+
+int simcuNumGrid(simcu_ *r) { return r ? r->ngrid : -1; }
+void *simcuDeviceOutput(simcu_ *r) { return r ? r->dOutGrid.p : nullptr; }
+
+int simcuGetStats(simcu_ *r, simcuStats_ *stats)
+{
+	if (!r || !stats) return -1;
+	if (r->ran && collectStats(r)) return -1;
+	*stats = r->stats;
+	return 0;
+}
+
+int simcuFetchRaw(simcu_ *r, int instance, double *data[], int *numPoints, int *numVariables)
+{
+	if (!r || !r->ran || !data || !numPoints) return -1;
+	const int rc = fetchRaw(r, instance, data, numPoints);
+	if (rc == 1) return fail("raw record overflow: %d points, raw_max_points = %d", *numPoints, r->rawMaxPoints);
+	if (numVariables) *numVariables = r->prog.N + 1;
+	return rc;
+}
+
+int simcuRunTransientBatch(simcu_ *r, double tstep, double tstop, double tmax, int restart,
+		char *probes[], int numProbes, double *data[], int *numGrid, int *status[],
+		simcuStats_ *stats)
+{
+	if (!r) return -1;
+	if (!restart && r->ran) return fail("continuing a finished batch (restart = 0) is not supported");
+	if (prepare(r, tstep, tstop, tmax, probes, numProbes, false)) return -1;
+	if (runDevice(r, 0, false)) return -1;
+	const size_t n = (size_t)r->M * r->ngrid * numProbes;
+	double *out = data ? (double *)std::malloc(sizeof(double) * std::max<size_t>(1, n)) : nullptr;
+	int *st = status ? (int *)std::malloc(sizeof(int) * r->M) : nullptr;
+	if ((data && !out) || (status && !st)) { std::free(out); std::free(st); return fail("out of memory"); }
+	if (simcuFetch(r, out, st, nullptr)) { std::free(out); std::free(st); return -1; }
+	if (data) *data = out;
+	if (status) *status = st;
+	if (numGrid) *numGrid = r->ngrid;
+	if (stats) return simcuGetStats(r, stats);
+	return 0;
+}
+
+int simcuRunTransient(simcu_ *r, double tstep, double tstop, double tmax, int restart,
+		int instance, double *data[], char **variables[], int *numPoints, int *numVariables)
+{
+	(void)restart;
+	return runSingle(r, false, tstep, tstop, tmax, instance, data, variables, numPoints, numVariables);
+}
+
+int simcuRunOperatingPoint(simcu_ *r, int instance, double *data[], char **variables[],
+		int *numPoints, int *numVariables)
+{
+	return runSingle(r, true, 0.0, 0.0, 0.0, instance, data, variables, numPoints, numVariables);
+}
+
+/* ---- introspection (host only) --------------------------------------------- */
+int simcuNumUnknowns(simcu_ *r) { return r ? (int)r->nl.rowName.size() - 1 : -1; }
+int simcuNumNonzeros(simcu_ *r) { return r ? (int)r->nl.nodes.size() : -1; }
+
+int simcuGetPattern(simcu_ *r, int *rowIdx, int *colStart)
+{
+	if (!r || !rowIdx || !colStart) return -1;
+	const int N = (int)r->nl.rowName.size() - 1;
+	for (int c = 0; c <= N; c++) colStart[c] = 0;
+	int k = 0;
+	for (std::set<std::pair<int, int> >::const_iterator it = r->nl.nodes.begin();
+			it != r->nl.nodes.end(); ++it, ++k) {
+		rowIdx[k] = it->second - 1;
+		colStart[it->first]++;
+	}
+	for (int c = 0; c < N; c++) colStart[c + 1] += colStart[c];
+	return 0;
+}
+
+const char *simcuVariableName(simcu_ *r, int k)
+{
+	if (!r || k < 0 || k + 1 >= (int)r->nl.rowName.size()) return nullptr;
+	return r->nl.rowName[k + 1].c_str();
+}
+
+int simcuGetPivots(simcu_ *r, int phase, int *pc, int *pr)
+{
+	if (!r || phase < 0 || phase > 1 || r->sched[phase].pc.empty()) return -1;
+	const Schedule &s = r->sched[phase];
+	for (size_t k = 0; k < s.pc.size(); k++) { pc[k] = s.pc[k]; pr[k] = s.pr[k]; }
+	return 0;
+}
+
+/* test hook: the symbolic analysis alone on caller-supplied matrices */
+int simcuSymbolic(int n, const int *colStart, const int *rowIdx, int numPilots,
+		const double *values, double threshold, int *pc, int *pr, int *numSlots,
+		int *numFactor)
+{
+	if (n < 1 || !colStart || !rowIdx || !values || numPilots < 1) return -1;
+	const int nnz = colStart[n];
+	std::vector<int> cs(colStart, colStart + n + 1), ri(rowIdx, rowIdx + nnz);
+	std::vector<std::vector<double> > pilots(numPilots);
+	for (int q = 0; q < numPilots; q++) pilots[q].assign(values + (size_t)q * nnz, values + (size_t)(q + 1) * nnz);
+	Schedule s;
+	std::string err;
+	if (!analyse(n, cs, ri, std::vector<char>(), pilots, threshold, nullptr, nullptr, s, err))
+		return fail("%s", err.c_str());
+	for (int k = 0; k < n; k++) { if (pc) pc[k] = s.pc[k]; if (pr) pr[k] = s.pr[k]; }
+	if (numSlots) *numSlots = s.F;
+	if (numFactor) *numFactor = s.nL + s.nU + n;
+	return 0;
+}
+
+namespace {
+struct EvalCtx { int n; const char **names; };
+int evalGetVar(void *ctx, const char *name)
+{
+	EvalCtx *e = (EvalCtx *)ctx;
+	for (int i = 0; i < e->n; i++) if (!std::strcmp(name, e->names[i])) return i;
+	return -1;
+}
+}
+
+int simcuCalcEval(const char *expr, int nvars, const char **names, const double *values,
+		double minDiv, int where, double *value, double *derivs)
+{
+	if (!expr || !value || (nvars > 0 && (!names || !values || !derivs))) return -1;
+	EvalCtx ctx; ctx.n = nvars; ctx.names = names;
+	CalcProg prog;
+	std::string err;
+	const int saveQuiet = gQuiet;
+	if (!calcCompile(expr, evalGetVar, &ctx, prog, err)) return -1;
+	const int nv = (int)prog.varNames.size();
+	std::vector<double> vals(std::max(1, nv)), out(1 + std::max(1, nv), 0.0);
+	for (int i = 0; i < nv; i++) vals[i] = values[prog.varRef[i]];
+	if (where == 0) {
+		double f, d;
+		calcRun(prog.code.data(), (int)prog.code.size(), prog.consts.data(), vals.data(), -1, minDiv, &f, &d);
+		out[0] = f;
+		for (int i = 0; i < nv; i++) {
+			calcRun(prog.code.data(), (int)prog.code.size(), prog.consts.data(), vals.data(), i, minDiv, &f, &d);
+			out[1 + i] = d;
+		}
+	} else {
+		DBuf dCode, dConst, dVals, dOut;
+		int rc = 0;
+		if (dCode.upload(prog.code) || dConst.upload(prog.consts) || dVals.upload(vals) ||
+				dOut.reserve(out.size() * 8))
+			rc = -1;
+		if (!rc && simcuLaunchCalc(dCode.as<int>(), (int)prog.code.size(), dConst.as<double>(),
+				dVals.as<double>(), nv, minDiv, dOut.as<double>(), nullptr))
+			rc = -1;
+		if (!rc && cudaMemcpy(out.data(), dOut.p, out.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+			rc = -1;
+		dCode.release(); dConst.release(); dVals.release(); dOut.release();
+		if (rc) { gQuiet = saveQuiet; return fail("device evaluation failed"); }
+	}
+	*value = out[0];
+	for (int i = 0; i < nvars; i++) derivs[i] = NAN;
+	for (int i = 0; i < nv; i++) derivs[prog.varRef[i]] = out[1 + i];
+	/* calc.c:47,96: a NaN result is an error */
+	if (std::isnan(out[0])) return -1;
+	for (int i = 0; i < nv; i++) if (std::isnan(out[1 + i])) return -1;
+	return 0;
+}
+
+}  /* extern "C" */

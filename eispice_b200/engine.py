@@ -1,0 +1,406 @@
+"""ctypes binding of ``libsimulator_cuda.so`` (include/simulator_cuda.h) -- the
+counterpart of the reference's ``module/simulatormodule.c``: it owns the
+parameter storage the C side borrows pointers into (simulatormodule.c:1423-1431
+passes ``&r->R``), attaches devices in netlist order and exposes the run calls.
+
+There is no fallback: if the shared library is missing it is built with
+``make`` (nvcc, sm_100a) and an import error is raised when that fails; every
+run call needs a CUDA device.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import waveform
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsimulator_cuda.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+STATUS = {0: "ok", 1: "timestep too small", 2: "singular matrix", 3: "NaN",
+          4: "operating point did not converge", 5: "T-line history too short",
+          6: "attempt budget exhausted"}
+
+_WAVE_NAMES = {cls.kind: cls._names for cls in (
+    waveform.Pulse, waveform.Gauss, waveform.Sin, waveform.Exp, waveform.SFFM)}
+
+
+class Stats(C.Structure):
+    """simcuStats_ (include/simulator_cuda.h)"""
+    _fields_ = [("accepted", C.c_longlong), ("rejectedLTE", C.c_longlong),
+                ("rejectedNC", C.c_longlong), ("factorizations", C.c_longlong),
+                ("opFactorizations", C.c_longlong), ("failed", C.c_longlong),
+                ("numUnknowns", C.c_int), ("numNonzeros", C.c_int),
+                ("numFactor", C.c_int), ("numFactorOP", C.c_int),
+                ("stateDoubles", C.c_int), ("histRows", C.c_int),
+                ("histRecords", C.c_int), ("workspaceInShared", C.c_int),
+                ("threadsPerBlock", C.c_int), ("kernelLaunches", C.c_int),
+                ("deviceMs", C.c_double), ("tranMs", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def build(force=False):
+    """Compile libsimulator_cuda.so in-tree (nvcc, sm_100a)."""
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    subprocess.run(["make", "-s", "-C", CSRC], check=True)
+    return LIB_PATH
+
+
+_lib = None
+_dpp = C.POINTER(C.POINTER(C.c_double))
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    L = C.CDLL(LIB_PATH)
+    vp, cp, dp, ip = C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.simcuNew.restype = vp
+    L.simcuNew.argtypes = [vp, C.c_int]
+    L.simcuDestroy.argtypes = [C.POINTER(vp)]
+    for f in ("simcuAddResistor", "simcuAddCapacitor", "simcuAddInductor"):
+        getattr(L, f).argtypes = [vp, cp, cp, cp, dp]
+    L.simcuAddNonlinearSource.argtypes = [vp, cp, cp, cp, C.c_char, cp]
+    L.simcuAddSource.argtypes = [vp, cp, cp, cp, C.c_char, dp, C.c_char, vp]
+    L.simcuAddTLine.argtypes = [vp, cp, cp, cp, cp, cp, dp, dp, dp]
+    L.simcuAddVICurve.argtypes = [vp, cp, cp, cp, vp, vp, C.c_char, vp, vp, C.c_char]
+    L.simcuSetInstanceParam.argtypes = [vp, cp, cp, vp, C.c_int]
+    L.simcuAddVITableSet.argtypes = [vp, cp, vp, vp, vp, vp]
+    L.simcuSetInstanceTableSet.argtypes = [vp, cp, vp, C.c_int]
+    L.simcuSetOption.argtypes = [vp, cp, C.c_double]
+    L.simcuSetPivots.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+    L.simcuRunTransient.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                    C.c_int, vp, vp, ip, ip]
+    L.simcuRunOperatingPoint.argtypes = [vp, C.c_int, vp, vp, ip, ip]
+    L.simcuRunTransientBatch.argtypes = [vp, C.c_double, C.c_double, C.c_double,
+                                         C.c_int, vp, C.c_int, vp, ip, vp, vp]
+    L.simcuPrepare.argtypes = [vp, C.c_double, C.c_double, C.c_double, vp, C.c_int]
+    L.simcuUpload.argtypes = [vp, vp]
+    L.simcuRunDevice.argtypes = [vp, vp]
+    L.simcuFetch.argtypes = [vp, vp, vp, vp]
+    L.simcuNumGrid.argtypes = [vp]
+    L.simcuDeviceOutput.restype = vp
+    L.simcuDeviceOutput.argtypes = [vp]
+    L.simcuGetStats.argtypes = [vp, vp]
+    L.simcuFetchRaw.argtypes = [vp, C.c_int, vp, ip, ip]
+    L.simcuNumUnknowns.argtypes = [vp]
+    L.simcuNumNonzeros.argtypes = [vp]
+    L.simcuGetPattern.argtypes = [vp, vp, vp]
+    L.simcuVariableName.restype = cp
+    L.simcuVariableName.argtypes = [vp, C.c_int]
+    L.simcuGetPivots.argtypes = [vp, C.c_int, vp, vp]
+    L.simcuSymbolic.argtypes = [C.c_int, vp, vp, C.c_int, vp, C.c_double, vp, vp, ip, ip]
+    L.simcuCalcEval.argtypes = [cp, C.c_int, vp, vp, C.c_double, C.c_int, dp, vp]
+    L.simcuFree.argtypes = [vp]
+    L.simcuSetDevice.argtypes = [C.c_int]
+    _lib = L
+    return L
+
+
+def _b(s):
+    return str(s).encode()
+
+
+def set_device(index):
+    if lib().simcuSetDevice(int(index)):
+        raise RuntimeError("simcuSetDevice(%d) failed" % index)
+
+
+class BatchResult:
+    """Probe waveforms of a batch on the ``tstep`` grid."""
+
+    def __init__(self, data, grid, status, stats, probes):
+        self.data = data          # [M, ngrid, nprobes]
+        self.grid = grid          # [ngrid]
+        self.status = status      # [M] simulator_cuda.h SIMCU_*
+        self.stats = stats        # dict of simcuStats_
+        self.probes = list(probes)
+
+    def __getitem__(self, probe):
+        return self.data[:, :, self.probes.index(probe)]
+
+
+def output_grid(tstep, tstop, ngrid):
+    g = np.arange(ngrid, dtype=np.float64) * tstep
+    g[-1] = tstop
+    return np.minimum(g, tstop)
+
+
+class Engine:
+    """One netlist topology, ``num_instances`` parameter sets, on the GPU."""
+
+    def __init__(self, netlist, num_instances=1):
+        self.L = lib()
+        self.num_instances = int(num_instances)
+        self.h = C.c_void_p(self.L.simcuNew(None, self.num_instances))
+        if not self.h:
+            raise RuntimeError("simcuNew failed")
+        self._keep = []
+        self._scalars = {}        # (refdes, member) -> c_double the C side borrows
+        self._kinds = {}          # refdes -> netlist tuple
+        self._attach(netlist)
+
+    # -- construction ------------------------------------------------------
+    def _dbl(self, refdes, name, value):
+        p = C.c_double(float(value))
+        self._scalars[(refdes, name)] = p
+        return C.byref(p)
+
+    def _tab(self, table):
+        t = np.ascontiguousarray(np.asarray(table, dtype=np.float64))
+        ptr = C.c_void_p(t.ctypes.data)
+        ln = C.c_int(len(t))
+        self._keep += [t, ptr, ln]
+        return C.cast(C.pointer(ptr), C.c_void_p), C.cast(C.pointer(ln), C.c_void_p)
+
+    def _attach(self, netlist):
+        L, h = self.L, self.h
+        for d in netlist:
+            k, ref = d[0], d[1]
+            self._kinds[ref] = d
+            if k in ("R", "C", "L"):
+                fn = {"R": L.simcuAddResistor, "C": L.simcuAddCapacitor,
+                      "L": L.simcuAddInductor}[k]
+                rc = fn(h, _b(ref), _b(d[2]), _b(d[3]), self._dbl(ref, k, d[4]))
+            elif k in ("V", "I"):
+                wave = d[6]
+                dc = self._dbl(ref, "DC", d[5])
+                if wave is None:
+                    rc = L.simcuAddSource(h, _b(ref), _b(d[2]), _b(d[3]), _b(d[4]),
+                                          dc, b"\0", None)
+                else:
+                    args = (C.c_void_p * 7)()
+                    if wave[0] in ("l", "c"):
+                        args[0], args[1] = self._tab(wave[1])
+                    else:
+                        for i, v in enumerate(wave[1]):
+                            args[i] = C.cast(self._dbl(ref, "A%d" % i, v), C.c_void_p)
+                    self._keep.append(args)
+                    rc = L.simcuAddSource(h, _b(ref), _b(d[2]), _b(d[3]), _b(d[4]),
+                                          dc, _b(wave[0]), args)
+            elif k == "B":
+                eq = C.create_string_buffer(_b(d[5]))
+                self._keep.append(eq)
+                rc = L.simcuAddNonlinearSource(h, _b(ref), _b(d[2]), _b(d[3]),
+                                               _b(d[4]), eq)
+            elif k == "T":
+                rc = L.simcuAddTLine(h, _b(ref), _b(d[2]), _b(d[3]), _b(d[4]), _b(d[5]),
+                                     self._dbl(ref, "Z0", d[6]), self._dbl(ref, "Td", d[7]),
+                                     self._dbl(ref, "loss", d[8]))
+            elif k == "VI":
+                vis, tas = d[4], d[5]
+                if tas and len(tas) != len(vis):
+                    raise ValueError("%s: VI and TA need the same number of table sets" % ref)
+                vp, vl = self._tab(vis[0][1])
+                tp, tl = self._tab(tas[0][1]) if tas else (None, None)
+                rc = L.simcuAddVICurve(h, _b(ref), _b(d[2]), _b(d[3]), vp, vl,
+                                       _b(vis[0][0]), tp, tl,
+                                       _b(tas[0][0]) if tas else b"l")
+                for s in range(1, len(vis)):
+                    if rc != 0:
+                        break
+                    vp, vl = self._tab(vis[s][1])
+                    tp, tl = self._tab(tas[s][1]) if tas else (None, None)
+                    rc = 0 if L.simcuAddVITableSet(h, _b(ref), vp, vl, tp, tl) == s else -1
+            else:
+                raise TypeError("unsupported device kind %r" % (k,))
+            if rc != 0:
+                raise RuntimeError("simulator_cuda rejected device %r" % (ref,))
+
+    def refresh_scalars(self, netlist):
+        """Re-read scalar members (the reference re-reads them through the
+        borrowed pointers at every deviceLoad)."""
+        for d in netlist:
+            k, ref = d[0], d[1]
+            if k in ("R", "C", "L"):
+                self._scalars[(ref, k)].value = float(d[4])
+            elif k in ("V", "I"):
+                self._scalars[(ref, "DC")].value = float(d[5])
+                if d[6] is not None and d[6][0] not in ("l", "c"):
+                    for i, v in enumerate(d[6][1]):
+                        self._scalars[(ref, "A%d" % i)].value = float(v)
+            elif k == "T":
+                for name, v in zip(("Z0", "Td", "loss"), d[6:9]):
+                    self._scalars[(ref, name)].value = float(v)
+
+    # -- options / parameters -------------------------------------------------
+    def set_option(self, name, value):
+        if self.L.simcuSetOption(self.h, _b(name), float(value)):
+            raise KeyError(name)
+
+    def c_name(self, refdes, attr):
+        """Member name of the Python device -> parameter name of the C-ABI."""
+        d = self._kinds[refdes]
+        if d[0] in ("V", "I") and attr != "DC":
+            wave = d[6]
+            if wave is None or wave[0] not in _WAVE_NAMES:
+                raise KeyError("%s.%s" % (refdes, attr))
+            return "A%d" % _WAVE_NAMES[wave[0]].index(attr)
+        return attr
+
+    def set_params(self, params):
+        """{"Refdes.attr": array[M]} -> per-instance values (copied)."""
+        M = self.num_instances
+        for key, vals in params.items():
+            refdes, attr = key.rsplit(".", 1)
+            if refdes not in self._kinds:
+                raise KeyError(key)
+            if attr == "set":
+                a = np.ascontiguousarray(np.broadcast_to(np.asarray(vals, dtype=np.int32), (M,)))
+                rc = self.L.simcuSetInstanceTableSet(self.h, _b(refdes), a.ctypes.data, 1)
+            else:
+                a = np.ascontiguousarray(np.broadcast_to(np.asarray(vals, dtype=np.float64), (M,)))
+                rc = self.L.simcuSetInstanceParam(self.h, _b(refdes),
+                                                  _b(self.c_name(refdes, attr)),
+                                                  a.ctypes.data, 1)
+            if rc != 0:
+                raise KeyError(key)
+
+    def set_pivots(self, phase, pc, pr):
+        pc = np.ascontiguousarray(pc, dtype=np.int32)
+        pr = np.ascontiguousarray(pr, dtype=np.int32)
+        self.L.simcuSetPivots(self.h, phase, pc.ctypes.data, pr.ctypes.data, len(pc))
+
+    # -- introspection ----------------------------------------------------------
+    def num_unknowns(self):
+        return self.L.simcuNumUnknowns(self.h)
+
+    def variables(self):
+        n = self.num_unknowns()
+        return ["time"] + [self.L.simcuVariableName(self.h, k).decode() for k in range(n)]
+
+    def pattern(self):
+        n = self.num_unknowns()
+        nnz = self.L.simcuNumNonzeros(self.h)
+        ri = np.zeros(nnz, dtype=np.int32)
+        cs = np.zeros(n + 1, dtype=np.int32)
+        self.L.simcuGetPattern(self.h, ri.ctypes.data, cs.ctypes.data)
+        return n, ri, cs
+
+    def pivots(self, phase):
+        n = self.num_unknowns()
+        pc = np.zeros(n, dtype=np.int32)
+        pr = np.zeros(n, dtype=np.int32)
+        if self.L.simcuGetPivots(self.h, phase, pc.ctypes.data, pr.ctypes.data):
+            raise RuntimeError("no pivot sequence yet (run first)")
+        return pc, pr
+
+    def stats(self):
+        st = Stats()
+        if self.L.simcuGetStats(self.h, C.byref(st)):
+            raise RuntimeError("simcuGetStats failed")
+        return st.as_dict()
+
+    # -- single-instance runs (reference result layout) ---------------------------
+    def _collect(self, rc, data, names, npts, nvar):
+        if rc != 0:
+            raise RuntimeError("simulator_cuda run failed")
+        arr = np.ctypeslib.as_array(data, shape=(npts.value, nvar.value)).copy()
+        var = [names[i].decode() for i in range(nvar.value)]
+        self.L.simcuFree(data)
+        self.L.simcuFree(names)
+        return arr, var
+
+    def tran_single(self, tstep, tstop, tmax=0.0, restart=True, instance=0):
+        data, names = C.POINTER(C.c_double)(), C.POINTER(C.c_char_p)()
+        npts, nvar = C.c_int(), C.c_int()
+        rc = self.L.simcuRunTransient(self.h, tstep, tstop, tmax, int(restart), instance,
+                                      C.byref(data), C.byref(names), C.byref(npts),
+                                      C.byref(nvar))
+        return self._collect(rc, data, names, npts, nvar)
+
+    def op_single(self, instance=0):
+        data, names = C.POINTER(C.c_double)(), C.POINTER(C.c_char_p)()
+        npts, nvar = C.c_int(), C.c_int()
+        rc = self.L.simcuRunOperatingPoint(self.h, instance, C.byref(data), C.byref(names),
+                                           C.byref(npts), C.byref(nvar))
+        return self._collect(rc, data, names, npts, nvar)
+
+    # -- batched runs ----------------------------------------------------------------
+    def _probe_array(self, probes):
+        arr = (C.c_char_p * max(1, len(probes)))(*[_b(p) for p in probes])
+        self._keep.append(arr)
+        return arr
+
+    def prepare(self, tstep, tstop, tmax=0.0, probes=()):
+        """One-off: compile, symbolic analysis on pilots, allocate, upload."""
+        self._run = (float(tstep), float(tstop), list(probes))
+        if self.L.simcuPrepare(self.h, tstep, tstop, tmax, self._probe_array(probes),
+                               len(probes)):
+            raise RuntimeError("simcuPrepare failed")
+        self.ngrid = self.L.simcuNumGrid(self.h)
+
+    def upload(self, stream=None):
+        if self.L.simcuUpload(self.h, stream):
+            raise RuntimeError("simcuUpload failed")
+
+    def run_device(self, stream=None):
+        if self.L.simcuRunDevice(self.h, stream):
+            raise RuntimeError("simcuRunDevice failed")
+
+    def fetch(self, data=None, status=None, stream=None):
+        """Device -> host copy of the gridded probes into ``data``
+        ([M, ngrid, nprobes] float64) and ``status`` ([M] int32)."""
+        M, nprobes = self.num_instances, len(self._run[2])
+        if data is None:
+            data = np.empty((M, self.ngrid, nprobes), dtype=np.float64)
+        if status is None:
+            status = np.empty(M, dtype=np.int32)
+        if self.L.simcuFetch(self.h, data.ctypes.data, status.ctypes.data, stream):
+            raise RuntimeError("simcuFetch failed")
+        return data, status
+
+    def device_output_ptr(self):
+        return self.L.simcuDeviceOutput(self.h)
+
+    def fetch_raw(self, instance):
+        data = C.POINTER(C.c_double)()
+        npts, nvar = C.c_int(), C.c_int()
+        if self.L.simcuFetchRaw(self.h, instance, C.byref(data), C.byref(npts), C.byref(nvar)):
+            raise RuntimeError("simcuFetchRaw failed")
+        arr = np.ctypeslib.as_array(data, shape=(npts.value, nvar.value)).copy()
+        self.L.simcuFree(data)
+        return arr
+
+    def tran_batch(self, tstep, tstop, tmax=0.0, params=None, probes=(), **options):
+        for k, v in options.items():
+            self.set_option(k, v)
+        if params:
+            self.set_params(params)
+        self.prepare(tstep, tstop, tmax, probes)
+        self.upload()
+        self.run_device()
+        data, status = self.fetch()
+        return BatchResult(data, output_grid(tstep, tstop, self.ngrid), status,
+                           self.stats(), probes)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.simcuDestroy(C.byref(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def calc_eval(expr, names, values, min_div=1e-15, where=0):
+    """(rc, value, derivs) of a B-source expression through the bytecode
+    compiler + interpreter; where = 0 host build of the interpreter, 1 GPU."""
+    n = len(names)
+    arr = (C.c_char_p * max(n, 1))(*[_b(x) for x in names])
+    vals = (C.c_double * max(n, 1))(*values)
+    val = C.c_double(0.0)
+    der = (C.c_double * max(n, 1))()
+    rc = lib().simcuCalcEval(_b(expr), n, arr, vals, min_div, where, C.byref(val), der)
+    return rc, val.value, list(der)[:n]

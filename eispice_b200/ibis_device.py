@@ -90,12 +90,15 @@ class Pin(subckt.Subckt):
         vcc = self.node("vcc")
         die = self.node("die")
         s0 = _aslist(speed)[0]
+        # one table set per (speed, direction) pair on EVERY VI device of the
+        # pin, so a single per-instance index selects a consistent corner
+        sets = corner_sets(speed, direction)
         self.Vcc = device.V(vcc, 0, model["voltage_range"][s0])
         mtype = model["model_type"]
         if mtype == "input" or (mtype == "i/o" and io == Input):
-            self.Buffer = Receiver(die, vcc, 0, model, speed)
+            self.Buffer = Receiver(die, vcc, 0, model, speed, sets=sets)
         elif mtype in ("output", "3-state", "i/o"):
-            self.Buffer = Driver(die, vcc, 0, model, speed, direction)
+            self.Buffer = Driver(die, vcc, 0, model, speed, direction, sets=sets)
         else:
             raise RuntimeError("Unsupported Model Type %s" % mtype)
         self.Package = Package(node, die, 0, pin)

@@ -1,0 +1,208 @@
+/*
+ * simulator_cuda.h - C-ABI of libs/simulator_cuda: the B200 batched transient
+ * engine behind eispice's simulator API.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8b.  The builder calls
+ * keep the names-by-position, argument meaning, pointer-borrowing and error
+ * convention of the reference's libs/simulator/include/simulator.h (cited per
+ * function), so that module/simulatormodule.c can call them with the very
+ * pointers it passes to simulatorAdd* today.  What is new is the instance
+ * dimension: one netlist topology, numInstances independent parameter sets.
+ *
+ * Conventions (reference libs/log/log.h:217-268): int 0 = ok, -1 = error,
+ * pointer NULL = error; a message goes to stderr.  Strings are copied; every
+ * double* / table pointer is BORROWED and re-read at the start of each run
+ * (reference: parameters are re-read at every deviceLoad).
+ * Not thread-safe per handle; one handle per Circuit.
+ *
+ * No torch types, no CUDA types: plain pointers and sizes.  `stream` arguments
+ * are a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef SIMULATOR_CUDA_H
+#define SIMULATOR_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMCU_MAJOR_VERSION 0
+#define SIMCU_MINOR_VERSION 1
+
+typedef struct _simcu simcu_;
+
+/* per-instance outcome (reference: any of these aborts the whole run,
+ * core/simulator.c:193-195,208-210, core/matrix.c:108-115; here the batch
+ * continues and the instance is flagged) */
+enum {
+	SIMCU_OK = 0,
+	SIMCU_ERR_TIMESTEP = 1,    /* "Timestep too small" */
+	SIMCU_ERR_SINGULAR = 2,    /* zero / non-finite pivot ("U is singular") */
+	SIMCU_ERR_NAN = 3,         /* NaN in a device evaluation */
+	SIMCU_ERR_OP = 4,          /* operating point did not converge (itl1) */
+	SIMCU_ERR_HISTORY = 5,     /* T-line history ring too short */
+	SIMCU_ERR_BUDGET = 6       /* attempt budget exhausted */
+};
+
+typedef struct {
+	long long accepted;        /* accepted timesteps, all instances */
+	long long rejectedLTE;     /* attempts rejected by the LTE test */
+	long long rejectedNC;      /* attempts rejected for non-convergence */
+	long long factorizations;  /* numeric LU + solve count (transient) */
+	long long opFactorizations;
+	long long failed;          /* instances with status != SIMCU_OK */
+	int numUnknowns;           /* N */
+	int numNonzeros;           /* nnz(A) */
+	int numFactor;             /* nnz(L+U-I) of the transient schedule */
+	int numFactorOP;           /* same for the operating-point schedule */
+	int stateDoubles;          /* per-instance device state (doubles) */
+	int histRows;              /* values per T-line history record */
+	int histRecords;           /* ring length */
+	int workspaceInShared;     /* 1: LU workspace is in shared memory */
+	int threadsPerBlock;
+	int kernelLaunches;        /* launches of the last simcuRunDevice */
+	double deviceMs;           /* device time of the last simcuRunDevice */
+	double tranMs;             /* of which: the transient kernel launches */
+} simcuStats_;
+
+/* simulatorNew (simulator.h:33): r must be NULL */
+simcu_ *simcuNew(simcu_ *r, int numInstances);
+/* simulatorDestroy (simulator.h:31) */
+int simcuDestroy(simcu_ **r);
+int simcuInfo(void);
+/* CUDA device for this thread's subsequent calls (one process per GPU) */
+int simcuSetDevice(int device);
+
+/* ---- builders: simulator.h:52-147, same argument lists ------------------- */
+/* simulatorAddResistor (simulator.h:52-55) */
+int simcuAddResistor(simcu_ *r, char *refdes, char *pNode, char *nNode,
+		double *resistance);
+/* simulatorAddCapacitor (simulator.h:57-60) */
+int simcuAddCapacitor(simcu_ *r, char *refdes, char *pNode, char *nNode,
+		double *capacitance);
+/* simulatorAddInductor (simulator.h:62-65) */
+int simcuAddInductor(simcu_ *r, char *refdes, char *pNode, char *nNode,
+		double *inductance);
+/* simulatorAddNonlinearSource (simulator.h:67-70): type 'i' 'v' 'c' */
+int simcuAddNonlinearSource(simcu_ *r, char *refdes, char *pNode, char *nNode,
+		char type, char *equation);
+/* simulatorAddSource (simulator.h:72-75): type 'v'/'i'; stimulus 0 'p' 's' 'e'
+ * 'l' 'c' 'f' 'g'; for 'l'/'c' args[0] is a double** table and args[1] an int*
+ * length (math/waveform.c:143-150) */
+int simcuAddSource(simcu_ *r, char *refdes, char *pNode, char *nNode,
+		char type, double *dc, char stimulus, double *args[7]);
+/* simulatorAddTLine (simulator.h:100-104) */
+int simcuAddTLine(simcu_ *r, char *refdes, char *pNodeLeft, char *nNodeLeft,
+		char *pNodeRight, char *nNodeRight, double *Z0, double *Td,
+		double *loss);
+/* simulatorAddVICurve (simulator.h:126-130) */
+int simcuAddVICurve(simcu_ *r, char *refdes, char *pNode, char *nNode,
+		double **vi, int *viLength, char viType,
+		double **ta, int *taLength, char taType);
+/* Not batchable (call back into the interpreter per Newton iteration /
+ * unfinished upstream): always -1.  simulator.h:77-98,106-124 */
+int simcuAddCallbackSource(simcu_ *r, char *refdes, char *pNode, char *nNode,
+		char type, char *variables[], double values[], double derivs[],
+		int numVariables, void *callback, void *private_);
+int simcuAddTLineW(simcu_ *r, char *refdes, char *nodes[], int nNodes, int *M,
+		double *len, double **L0, double **C0, double **R0, double **G0,
+		double **Rs, double **Gd, double *fgd, double *fK);
+
+/* ---- the instance dimension (additive) ----------------------------------- */
+/* Per-instance values of a scalar parameter: name is the binding's member name
+ * (R C L DC Z0 Td loss, or A0..A6 = waveform argument slot).  values[i*stride]
+ * is instance i; stride 0 broadcasts.  Copied immediately. */
+int simcuSetInstanceParam(simcu_ *r, char *refdes, char *name,
+		const double *values, int stride);
+/* Further table sets (e.g. IBIS corners) for an existing VI device; returns
+ * the set index (>= 1) or -1.  Tables are borrowed like simcuAddVICurve's. */
+int simcuAddVITableSet(simcu_ *r, char *refdes, double **vi, int *viLength,
+		double **ta, int *taLength);
+/* Which table set each instance uses (default 0). Copied immediately. */
+int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
+		int stride);
+/* Options: reltol vntol abstol captol chgtol trtol gmin itl1 itl4 maxorder
+ * minstep (control.h:34-56); hist_records, max_attempts, attempts_per_launch,
+ * threads_per_block, workspace_shared (0/1), raw_max_points, raw_first,
+ * raw_count, pivot_threshold, num_pilots; r = NULL: quiet (0/1) */
+int simcuSetOption(simcu_ *r, char *name, double value);
+/* Force the pivot sequence of a phase (0 = operating point, 1 = transient)
+ * instead of the built-in pilot analysis: step k eliminates column pc[k] with
+ * pivot row pr[k] (0-based unknowns).  This is where a build inside eispice
+ * feeds perm_c / perm_r of its own libs/superlu (dgssvx, core/matrix.c:82-118;
+ * SURVEY.md appendix B).  pc = NULL returns to the built-in analysis. */
+int simcuSetPivots(simcu_ *r, int phase, const int *pc, const int *pr, int n);
+
+/* ---- runs ----------------------------------------------------------------- */
+/* simulatorRunTransient (simulator.h:35-38) for ONE instance (index
+ * `instance`), same result layout: *data is malloc'd [numPoints][numVariables]
+ * row-major with column 0 = time, *variables is a malloc'd NULL-terminated
+ * array (strings owned by the handle). Free both with simcuFree. */
+int simcuRunTransient(simcu_ *r, double tstep, double tstop, double tmax,
+		int restart, int instance, double *data[], char **variables[],
+		int *numPoints, int *numVariables);
+/* simulatorRunOperatingPoint (simulator.h:40-42) for one instance */
+int simcuRunOperatingPoint(simcu_ *r, int instance, double *data[],
+		char **variables[], int *numPoints, int *numVariables);
+
+/* Batched transient, HOST buffers in and out (the e2e path): uploads the
+ * per-instance parameters, runs every instance with its own adaptive step
+ * control, resamples the probes onto the grid t_g = g*tstep (g = 0..numGrid-1,
+ * last point tstop) by linear interpolation and downloads the result.
+ *   probes[numProbes]  result names, "v(node)" / "i(refdes)"
+ *   *data              malloc'd [numInstances][numGrid][numProbes]
+ *   *status            malloc'd [numInstances] (SIMCU_*)
+ * stats may be NULL. */
+int simcuRunTransientBatch(simcu_ *r, double tstep, double tstop, double tmax,
+		int restart, char *probes[], int numProbes, double *data[],
+		int *numGrid, int *status[], simcuStats_ *stats);
+
+/* The same run in stages, for callers that keep data on the device:
+ *   Prepare  one-off: compile the netlist, symbolic LU analysis on a pilot
+ *            batch, allocate device state, upload tables
+ *   Upload   host -> device copy of the per-instance parameters
+ *   RunDevice  all kernels of one batched transient on `stream`
+ *   Fetch    device -> host copy of the gridded probes ([M][numGrid][numProbes])
+ *            and status; either pointer may be NULL */
+int simcuPrepare(simcu_ *r, double tstep, double tstop, double tmax,
+		char *probes[], int numProbes);
+int simcuUpload(simcu_ *r, void *stream);
+int simcuRunDevice(simcu_ *r, void *stream);
+int simcuFetch(simcu_ *r, double *data, int *status, void *stream);
+int simcuNumGrid(simcu_ *r);
+/* device pointer of the gridded output, layout [numGrid][numProbes][M] */
+void *simcuDeviceOutput(simcu_ *r);
+int simcuGetStats(simcu_ *r, simcuStats_ *stats);
+/* raw (time, X) record of one instance of the last batch, reference layout
+ * (core/matrix.c:430-470): malloc'd [numPoints][numVariables], column 0 = time.
+ * Needs the options raw_max_points > 0 and raw_first / raw_count covering it. */
+int simcuFetchRaw(simcu_ *r, int instance, double *data[], int *numPoints,
+		int *numVariables);
+
+/* ---- introspection (host only, no GPU needed) ----------------------------- */
+int simcuNumUnknowns(simcu_ *r);
+int simcuNumNonzeros(simcu_ *r);
+/* CSC pattern in the reference's order (core/node.c:56-66, matrix.c:476-497) */
+int simcuGetPattern(simcu_ *r, int *rowIdx, int *colStart);
+/* name of unknown k (0-based), e.g. "v(out)"; owned by the handle */
+const char *simcuVariableName(simcu_ *r, int k);
+/* fixed pivot sequence chosen by Prepare: phase 0 = operating point,
+ * 1 = transient; step k eliminates column pc[k] with pivot row pr[k] */
+int simcuGetPivots(simcu_ *r, int phase, int *pc, int *pr);
+/* test hook: the symbolic analysis alone.  CSC pattern + numPilots value sets
+ * ([numPilots][nnz]) in, pivot sequence, workspace slots and nnz(L+U-I) out */
+int simcuSymbolic(int n, const int *colStart, const int *rowIdx, int numPilots,
+		const double *values, double threshold, int *pc, int *pr, int *numSlots,
+		int *numFactor);
+/* test hook: compile `expr` to device bytecode and evaluate it with the
+ * device interpreter on `where` = 0 host build of the same code / 1 GPU.
+ * Same contract as the reference's calcSolve + calcDiff per variable. */
+int simcuCalcEval(const char *expr, int nvars, const char **names,
+		const double *values, double minDiv, int where, double *value,
+		double *derivs);
+
+void simcuFree(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

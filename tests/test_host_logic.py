@@ -1,0 +1,278 @@
+"""Host side of libsimulator_cuda without a GPU: the library loads and exports
+every symbol of include/simulator_cuda.h, the netlist builder creates the
+reference's rows and sparsity pattern (checked against the oracle, which is
+pinned to the reference), the expression compiler + interpreter agree with the
+reference's calculon (golden vectors + fuzz against the oracle), and the
+symbolic LU analysis yields usable pivot sequences."""
+import json
+import math
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import backends
+import circuits
+from eispice_b200 import engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    lib = engine.lib()
+    hdr = open(os.path.join(ROOT, "include", "simulator_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(simcu[A-Z]\w*)\s*\(", hdr))
+    assert len(names) >= 30
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+
+
+@pytest.mark.parametrize("name", sorted(circuits.all_cases()))
+def test_rows_and_pattern_match_reference_order(name):
+    build = circuits.all_cases()[name][0]
+    nl = build().netlist()
+    eng = engine.Engine(nl, 1)
+    ora = backends.OracleSim(nl)
+    n, ri, cs = eng.pattern()
+    n2, ri2, cs2 = ora.pattern()
+    assert n == n2
+    assert np.array_equal(cs, cs2) and np.array_equal(ri, ri2)
+    # names: run-free comparison through a tiny OP on the oracle
+    _, names = ora.op() if True else (None, None)
+    assert eng.variables() == names
+    eng.close()
+
+
+def test_multiple_table_sets_keep_the_pattern():
+    cct = circuits._new("sets")
+    import eispice_b200 as eispice
+    t1 = eispice.PWL([[-1, -1], [0, 0], [1, 2]])
+    t2 = eispice.PWL([[-1, -2], [0, 0], [1, 3]])
+    cct.Vx = eispice.V(1, 0, 1)
+    cct.VIx = eispice.VI(1, 0, [t1, t2])
+    eng = engine.Engine(cct.netlist(), 4)
+    eng.set_params({"VIx.set": np.array([0, 1, 1, 0])})
+    with pytest.raises(KeyError):
+        eng.set_params({"VIx.bogus": np.zeros(4)})
+    assert eng.num_unknowns() == 4
+    eng.close()
+
+
+def test_rejects_what_the_reference_rejects():
+    L = engine.lib()
+    import ctypes as C
+    L.simcuSetOption(None, b"quiet", 1.0)
+    try:
+        h = C.c_void_p(L.simcuNew(None, 1))
+        one = C.c_double(1.0)
+        assert L.simcuAddResistor(h, b"R1", b"a", b"0", C.byref(one)) == 0
+        assert L.simcuAddResistor(h, b"R1", b"a", b"b", C.byref(one)) == -1      # listed twice
+        assert L.simcuAddSource(h, b"V1", b"0", b"0", b"v", C.byref(one), b"\0", None) == -1
+        assert L.simcuAddSource(h, b"V2", b"a", b"0", b"x", C.byref(one), b"\0", None) == -1
+        assert L.simcuAddTLine(h, b"T1", b"0", b"0", b"b", b"0", C.byref(one), C.byref(one),
+                               C.byref(one)) == -1
+        eq = C.create_string_buffer(b"foo + 1")
+        assert L.simcuAddNonlinearSource(h, b"B1", b"a", b"0", b"i", eq) == -1   # bare variable
+        eq2 = C.create_string_buffer(b"v(a) * ")
+        assert L.simcuAddNonlinearSource(h, b"B2", b"a", b"0", b"i", eq2) == -1  # syntax
+        assert L.simcuAddCallbackSource(h, b"P1", b"a", b"0", b"i", None, None, None, 0,
+                                        None, None) == -1
+        assert L.simcuNew(h, 1) is None                                          # arg must be NULL
+        L.simcuDestroy(C.byref(h))
+    finally:
+        L.simcuSetOption(None, b"quiet", 0.0)
+
+
+# ---- expression compiler ---------------------------------------------------
+VEC = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "calc_vectors.json")))
+
+
+def _same(a, b, rel=1e-12):
+    if a is None or b is None:
+        return a is None and b is None
+    if math.isnan(a) or math.isnan(b):
+        return math.isnan(a) and math.isnan(b)
+    if math.isinf(a) or math.isinf(b):
+        return a == b
+    return abs(a - b) <= rel * max(abs(a), abs(b)) + 1e-300
+
+
+def test_bytecode_matches_reference_golden_vectors():
+    names = VEC["names"]
+    for case in VEC["cases"]:
+        rc, val, der = engine.calc_eval(case["expr"], names, case["values"])
+        assert (rc == 0) == case["ok"], case["expr"]
+        if rc == 0:
+            assert _same(val, case["value"]), (case["expr"], val, case["value"])
+            for d, g in zip(der, case["derivs"]):
+                assert _same(None if math.isnan(d) else d, g), (case["expr"], der, case["derivs"])
+
+
+def _random_expr(rng, depth=0):
+    atoms = ["v(a)", "v(b)", "i(Vx)", "time", "2", "0.5", "1m", "3k", "1e-3", "v(a,b)",
+             "2.5Meg", "4mil", "7u"]
+    funcs = ["abs", "sin", "cos", "exp", "sqrt", "uramp", "u", "atan", "sinh", "ln", "log",
+             "tan", "cosh", "asinh"]
+    if depth > 3 or rng.random() < 0.25:
+        return rng.choice(atoms)
+    r = rng.random()
+    if r < 0.45:
+        return "%s %s %s" % (_random_expr(rng, depth + 1), rng.choice("+-*/^"),
+                             _random_expr(rng, depth + 1))
+    if r < 0.6:
+        return "%s(%s)" % (rng.choice(funcs), _random_expr(rng, depth + 1))
+    if r < 0.7:
+        return "(%s)" % _random_expr(rng, depth + 1)
+    if r < 0.78:
+        return "-%s" % _random_expr(rng, depth + 1)
+    if r < 0.86:
+        return "%s(%s)" % (_random_expr(rng, depth + 1), _random_expr(rng, depth + 1))
+    if r < 0.93:
+        return "if(%s %s %s)" % (_random_expr(rng, depth + 1),
+                                 rng.choice([">", "<", ">=", "<=", "==", "!="]),
+                                 _random_expr(rng, depth + 1))
+    return "if((%s > %s) %s (%s < %s))" % (
+        _random_expr(rng, depth + 1), _random_expr(rng, depth + 1), rng.choice(["&&", "||"]),
+        _random_expr(rng, depth + 1), _random_expr(rng, depth + 1))
+
+
+def test_bytecode_fuzz_against_oracle():
+    rng = random.Random(20261)
+    names = ["v(a)", "v(b)", "i(Vx)", "time"]
+    agree = 0
+    for _ in range(1500):
+        expr = _random_expr(rng)
+        values = [rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-1, 1), rng.uniform(0, 1e-6)]
+        rc_o, v_o, d_o = backends.eval_expr("oracle", expr, names, values)
+        rc_e, v_e, d_e = engine.calc_eval(expr, names, values)
+        assert (rc_o == 0) == (rc_e == 0), (expr, values, rc_o, rc_e)
+        if rc_o == 0:
+            assert _same(v_o, v_e), (expr, values, v_o, v_e)
+            for a, b in zip(d_o, d_e):
+                assert _same(a, b), (expr, values, d_o, d_e)
+            agree += 1
+    assert agree > 300
+
+
+def test_expression_limits():
+    deep = "(" * 30 + "v(a)" + ")" * 30                     # nesting alone costs no stack
+    assert engine.calc_eval(deep, ["v(a)"], [1.5])[0] == 0
+    chain = "+".join(["(v(a)*" * 30 + "1" + ")" * 30])        # 31 live operands
+    assert engine.calc_eval(chain, ["v(a)"], [1.0])[0] == -1
+
+
+# ---- symbolic analysis -----------------------------------------------------
+def _dense_solve_with_pivots(A, b, pc, pr):
+    """Replay a fixed (column, row) sequence densely -- what the kernel does."""
+    W = A.copy()
+    y = b.copy()
+    n = len(b)
+    rdone = np.zeros(n, bool)
+    cdone = np.zeros(n, bool)
+    for k in range(n):
+        c, p = pc[k], pr[k]
+        rdone[p] = True
+        cdone[c] = True
+        for r in range(n):
+            if rdone[r]:
+                continue
+            l = W[r, c] / W[p, c]
+            W[r, ~cdone] -= l * W[p, ~cdone]
+            y[r] -= l * y[p]
+    x = np.zeros(n)
+    for k in range(n - 1, -1, -1):
+        c, p = pc[k], pr[k]
+        acc = y[p]
+        for j in range(k + 1, n):
+            acc -= W[p, pc[j]] * x[pc[j]]
+        x[c] = acc / W[p, c]
+    return x
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_symbolic_analysis_on_mna_like_matrices(seed):
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(5, 40))
+    # conductance-like block with zero-diagonal branch rows (voltage sources)
+    S = np.zeros((n, n), bool)
+    for i in range(n):
+        S[i, i] = rng.random() < 0.8
+    for _ in range(3 * n):
+        i, j = rng.integers(0, n, 2)
+        S[i, j] = S[j, i] = True
+    nb = max(1, n // 5)
+    for k in range(nb):            # branch k couples to node k with +-1, zero diagonal
+        b = n - 1 - k
+        S[b, :] = False
+        S[:, b] = False
+        S[b, k] = S[k, b] = True
+    pilots = []
+    for q in range(3):
+        A = np.where(S, rng.uniform(0.5, 2.0, (n, n)) * 10.0 ** rng.integers(-3, 3, (n, n)), 0.0)
+        for i in range(n - nb):
+            A[i, i] = np.abs(A[i]).sum() + 1.0
+            S[i, i] = True
+        for k in range(nb):
+            b = n - 1 - k
+            A[b, k] = 1.0
+            A[k, b] = 1.0
+        pilots.append(A)
+    cs = [0]
+    ri = []
+    for c in range(n):
+        rows = np.nonzero(S[:, c])[0]
+        ri += list(rows)
+        cs.append(len(ri))
+    cs = np.array(cs, dtype=np.int32)
+    ri = np.array(ri, dtype=np.int32)
+    vals = np.array([[A[r, c] for c in range(n) for r in np.nonzero(S[:, c])[0]] for A in pilots])
+    pc = np.zeros(n, dtype=np.int32)
+    pr = np.zeros(n, dtype=np.int32)
+    slots, nf = C.c_int(), C.c_int()
+    rc = engine.lib().simcuSymbolic(n, cs.ctypes.data, ri.ctypes.data, len(pilots),
+                                    np.ascontiguousarray(vals).ctypes.data, 0.1,
+                                    pc.ctypes.data, pr.ctypes.data, C.byref(slots), C.byref(nf))
+    assert rc == 0
+    assert sorted(pc) == list(range(n)) and sorted(pr) == list(range(n))
+    assert slots.value >= len(ri) and nf.value >= n
+    for A in pilots:
+        b = rng.normal(size=n)
+        x = _dense_solve_with_pivots(A, b, pc, pr)
+        assert np.allclose(A @ x, b, rtol=1e-8, atol=1e-8 * np.abs(b).max())
+
+
+def test_symbolic_analysis_reports_singular():
+    import ctypes as C
+    L = engine.lib()
+    L.simcuSetOption(None, b"quiet", 1.0)
+    try:
+        cs = np.array([0, 1, 2], dtype=np.int32)
+        ri = np.array([0, 0], dtype=np.int32)       # both entries in row 0
+        vals = np.array([1.0, 2.0])
+        pc = np.zeros(2, dtype=np.int32)
+        pr = np.zeros(2, dtype=np.int32)
+        rc = L.simcuSymbolic(2, cs.ctypes.data, ri.ctypes.data, 1, vals.ctypes.data, 0.1,
+                             pc.ctypes.data, pr.ctypes.data, None, None)
+        assert rc == -1
+    finally:
+        L.simcuSetOption(None, b"quiet", 0.0)
+
+
+def test_runs_fail_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = engine.lib()
+    L.simcuSetOption(None, b"quiet", 1.0)
+    try:
+        cct = circuits.cfg1_rc()
+        with pytest.raises(RuntimeError):
+            cct.tran('0.01n', '10n')
+        with pytest.raises(RuntimeError):
+            cct.tran_batch('0.01n', '10n', probes=["v(out)"])
+    finally:
+        L.simcuSetOption(None, b"quiet", 0.0)
