@@ -597,6 +597,14 @@ int analysePhase(simcu_ *r, int ph)
 {
 	std::vector<std::vector<double> > pilots;
 	if (downloadPilots(r, pilots)) return -1;
+	/* an instance with a non-finite stamp (R = 0, NaN parameter) fails on its
+	 * own later; it must not decide the pivots of the others */
+	for (size_t q = 0; q < pilots.size();) {
+		bool finite = true;
+		for (size_t s = 0; s < pilots[q].size(); s++) finite = finite && std::isfinite(pilots[q][s]);
+		if (finite) q++; else pilots.erase(pilots.begin() + q);
+	}
+	if (pilots.empty()) return fail("every pilot instance has non-finite matrix entries");
 	std::string err;
 	const Program &p = r->prog;
 	const bool forced = !r->forcePc[ph].empty();

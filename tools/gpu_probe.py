@@ -27,6 +27,7 @@ def main():
     backends.build_oracle()
     only = sys.argv[1:]
     report = {}
+    dump = {}
     for name, (build, an, checks) in sorted(circuits.all_cases().items()):
         if only and name not in only:
             continue
@@ -67,6 +68,8 @@ def main():
                 idx = [var.index(v) for v in rvar]
                 line["grid_vs_ref"] = float("%.3g" % parity.grid_error(
                     data[:, 0], data[:, idx], ref[:, 0], ref, rvar, tstep, tstop))
+            dump[name] = data
+            dump[name + "__oracle"] = od
             ok = True
             for kind, node, value, tm in checks:
                 col = var.index("%s(%s)" % (kind, node))
@@ -84,6 +87,7 @@ def main():
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     json.dump(report, open(os.path.join(out, "probe.json"), "w"), indent=1)
+    np.savez_compressed(os.path.join(out, "probe_data.npz"), **dump)
 
 
 if __name__ == "__main__":

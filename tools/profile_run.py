@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""One batched transient of a workload, for ncu: prepare, one warm-up run, one
+profiled run.  Usage: profile_run.py <cfg> <instances> [tpb]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import workloads  # noqa: E402
+from eispice_b200 import engine  # noqa: E402
+
+name, M = sys.argv[1], int(sys.argv[2])
+w = workloads.make(name, M)
+eng = engine.Engine(w.cct.netlist(), w.M)
+if len(sys.argv) > 3:
+    eng.set_option("threads_per_block", int(sys.argv[3]))
+eng.set_params(w.params)
+eng.prepare(w.tstep, w.tstop, 0.0, w.probes)
+eng.upload()
+for _ in range(2):
+    eng.run_device()
+st = eng.stats()
+print({k: st[k] for k in ("accepted", "factorizations", "failed", "deviceMs", "tranMs",
+                          "threadsPerBlock", "numFactor")})
