@@ -15,10 +15,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "simcu_calc.h"
+#include "simcu_codegen.h"
 #include "simcu_host.h"
 #include "simcu_kernels.h"
 
@@ -97,6 +100,12 @@ struct _simcu {
 	std::vector<std::string> probeNames;
 	std::vector<int> probeRows;
 	int ngrid = 0, histRecords = 0, tpb = 64, wsShared = 1;
+	int interpreter = 0;            /* 1: run the batch on the generic kernels */
+	int maxRegs = 0;
+	std::vector<char> active[2];
+	std::shared_ptr<JitKernel> jit;
+	std::vector<int> jitProbes;
+	int jitTpb = 0, jitBlocks = 0;
 	SimcuArgs args[2];
 	simcuStats_ stats;
 	/* device memory */
@@ -485,6 +494,8 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "raw_count") r->rawCount = (int)value;
 	else if (n == "pivot_threshold") { r->pivotThreshold = value; r->sched[0].lu.clear(); r->sched[1].lu.clear(); }
 	else if (n == "num_pilots") r->numPilots = std::max(1, (int)value);
+	else if (n == "interpreter") r->interpreter = (value != 0.0);
+	else if (n == "max_registers") { r->maxRegs = (int)value; r->jit.reset(); }
 	else return fail("unknown option %s", name);
 	r->prepared = false;
 	return 0;
@@ -505,7 +516,7 @@ int simcuSetPivots(simcu_ *r, int phase, const int *pc, const int *pr, int n)
 }  /* extern "C" */
 
 /* ------------------------------------------------------------------------ *
- * Preparation: compile, upload, allocate, symbolic analysis on pilots
+ * Preparation: flatten, symbolic analysis on a pilot batch, NVRTC, allocate
  * ------------------------------------------------------------------------ */
 namespace {
 
@@ -516,6 +527,7 @@ int ensureCompiled(simcu_ *r)
 		if (!compileProgram(r->nl, r->M, r->prog, err)) return fail("%s", err.c_str());
 		r->compiled = true;
 		r->sched[0] = Schedule(); r->sched[1] = Schedule();
+		r->jit.reset();
 	} else if (!refreshParameters(r->nl, r->M, r->prog, err)) {
 		return fail("%s", err.c_str());
 	}
@@ -553,14 +565,14 @@ int uploadSchedule(simcu_ *r, int ph)
 	return 0;
 }
 
-/* threads per block and where the LU workspace lives */
-int chooseLaunchShape(simcu_ *r)
+/* generic kernels: threads per block and where their LU workspace lives */
+int genericShape(simcu_ *r, int M, int wantTpb, int *tpbOut, int *sharedOut, DBuf &ws)
 {
 	const int words = std::max(r->sched[0].F, r->sched[1].F) + r->prog.N;
 	int dev = 0, maxSmem = 0;
 	CU(cudaGetDevice(&dev));
 	CU(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-	int tpb = r->tpbOpt > 0 ? r->tpbOpt : 64;
+	int tpb = wantTpb > 0 ? wantTpb : 64;
 	tpb = std::max(32, (tpb / 32) * 32);
 	int shared = (r->wsSharedOpt < 0) ? 1 : r->wsSharedOpt;
 	if (shared) {
@@ -568,57 +580,135 @@ int chooseLaunchShape(simcu_ *r)
 		if ((size_t)words * tpb * 8 > (size_t)maxSmem) {
 			if (r->wsSharedOpt == 1) return fail("LU workspace does not fit shared memory");
 			shared = 0;
-			tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 128;
+			tpb = wantTpb > 0 ? std::max(32, (wantTpb / 32) * 32) : 128;
 		}
 	}
-	r->tpb = tpb; r->wsShared = shared;
-	if (!shared && r->dWs.reserve((size_t)words * r->M * 8)) return -1;
-	for (int ph = 0; ph < 2; ph++) {
-		r->args[ph].wsShared = shared;
-		r->args[ph].wsGlobal = r->dWs.as<double>();
-	}
+	if (!shared && ws.reserve((size_t)words * M * 8)) return -1;
+	*tpbOut = tpb; *sharedOut = shared;
 	return 0;
 }
 
-int downloadPilots(simcu_ *r, std::vector<std::vector<double> > &pilots)
-{
-	const int M = r->M, nnz = r->prog.nnzA;
-	const int P = std::min(M, r->numPilots);
-	pilots.assign(P, std::vector<double>(nnz));
-	for (int q = 0; q < P; q++) {
-		const int i = (P > 1) ? (int)((long long)q * (M - 1) / (P - 1)) : 0;
-		CU(cudaMemcpy2D(pilots[q].data(), sizeof(double), r->dA.as<double>() + i,
-				(size_t)M * sizeof(double), sizeof(double), nnz, cudaMemcpyDeviceToHost));
-	}
-	return 0;
-}
+/* The pilot pass: a compact batch of up to numPilots instances spread over the
+ * sweep runs through the generic kernels - load, then (for the transient
+ * phase) operating point and the assembly of the first attempt - and the
+ * matrices it leaves behind decide the pivot sequences of both phases. */
+struct Pilot {
+	DBuf A, B, X, S, IS, CD, CI, Ht, Hx, pinst, iinst, remaining, ws;
+};
 
-int analysePhase(simcu_ *r, int ph)
+int analyseFrom(simcu_ *r, int ph, const DBuf &dA, int P)
 {
+	const Program &p = r->prog;
+	std::vector<double> flat((size_t)p.nnzA * P);
+	CU(cudaMemcpy(flat.data(), dA.p, flat.size() * 8, cudaMemcpyDeviceToHost));
 	std::vector<std::vector<double> > pilots;
-	if (downloadPilots(r, pilots)) return -1;
-	/* an instance with a non-finite stamp (R = 0, NaN parameter) fails on its
-	 * own later; it must not decide the pivots of the others */
-	for (size_t q = 0; q < pilots.size();) {
+	for (int q = 0; q < P; q++) {
+		std::vector<double> v(p.nnzA);
 		bool finite = true;
-		for (size_t s = 0; s < pilots[q].size(); s++) finite = finite && std::isfinite(pilots[q][s]);
-		if (finite) q++; else pilots.erase(pilots.begin() + q);
+		for (int s = 0; s < p.nnzA; s++) { v[s] = flat[(size_t)s * P + q]; finite = finite && std::isfinite(v[s]); }
+		/* an instance with a non-finite stamp (R = 0, NaN parameter) fails on
+		 * its own later; it must not decide the pivots of the others */
+		if (finite) pilots.push_back(v);
 	}
 	if (pilots.empty()) return fail("every pilot instance has non-finite matrix entries");
-	std::string err;
-	const Program &p = r->prog;
-	const bool forced = !r->forcePc[ph].empty();
-	if (forced && (int)r->forcePc[ph].size() != p.N) return fail("forced pivot sequence has the wrong length");
 	/* a slot the flattener believes is exactly zero in this phase must be */
 	std::vector<char> active = ph ? p.activeTran : p.activeOP;
 	for (size_t q = 0; q < pilots.size(); q++)
 		for (int s = 0; s < p.nnzA; s++)
 			if (!active[s] && pilots[q][s] != 0.0) active[s] = 1;
-	if (!analyse(p.N, p.colStart, p.rowIdx, active, pilots,
-			r->pivotThreshold, forced ? r->forcePc[ph].data() : nullptr,
-			forced ? r->forcePr[ph].data() : nullptr, r->sched[ph], err))
+	r->active[ph] = active;
+	const bool forced = !r->forcePc[ph].empty();
+	if (forced && (int)r->forcePc[ph].size() != p.N) return fail("forced pivot sequence has the wrong length");
+	std::string err;
+	if (!analyse(p.N, p.colStart, p.rowIdx, active, pilots, r->pivotThreshold,
+			forced ? r->forcePc[ph].data() : nullptr, forced ? r->forcePr[ph].data() : nullptr,
+			r->sched[ph], err))
 		return fail("%s analysis: %s", ph ? "transient" : "operating-point", err.c_str());
+	r->jit.reset();
 	return uploadSchedule(r, ph);
+}
+
+int pilotPass(simcu_ *r, bool needOP, bool needTran)
+{
+	const Program &p = r->prog;
+	const int M = r->M, P = std::min(M, r->numPilots);
+	std::vector<int> idx(P);
+	for (int q = 0; q < P; q++) idx[q] = (P > 1) ? (int)((long long)q * (M - 1) / (P - 1)) : 0;
+	std::vector<double> pin((size_t)p.ninst * P);
+	std::vector<int> iin((size_t)p.niinst * P);
+	for (int k = 0; k < p.ninst; k++)
+		for (int q = 0; q < P; q++) pin[(size_t)k * P + q] = p.pinst[(size_t)k * M + idx[q]];
+	for (int k = 0; k < p.niinst; k++)
+		for (int q = 0; q < P; q++) iin[(size_t)k * P + q] = p.iinst[(size_t)k * M + idx[q]];
+	Pilot b;
+	const int nh = (int)p.histRows.size(), R = 8;
+	const size_t m8 = (size_t)P * 8, m4 = (size_t)P * 4;
+	int rc = -1;
+	do {
+		if (b.pinst.upload(pin) || b.iinst.upload(iin) || b.A.reserve(p.nnzA * m8) ||
+				b.B.reserve(p.N * m8) || b.X.reserve(p.N * m8) ||
+				b.S.reserve(std::max(1, p.stateDoubles) * m8) ||
+				b.IS.reserve(std::max(1, p.stateInts) * m4) || b.CD.reserve(CD_NUM * m8) ||
+				b.CI.reserve(CI_NUM * m4) || b.Ht.reserve(R * m8) ||
+				b.Hx.reserve((size_t)R * std::max(1, nh) * m8) || b.remaining.reserve(sizeof(int)))
+			break;
+		if (cudaMemset(b.S.p, 0, std::max(1, p.stateDoubles) * m8) != cudaSuccess ||
+				cudaMemset(b.IS.p, 0, std::max(1, p.stateInts) * m4) != cudaSuccess)
+			break;
+		SimcuArgs a = r->args[0];
+		a.M = P; a.pinst = b.pinst.as<double>(); a.iinst = b.iinst.as<int>();
+		a.A = b.A.as<double>(); a.B = b.B.as<double>(); a.X = b.X.as<double>();
+		a.S = b.S.as<double>(); a.IS = b.IS.as<int>(); a.CD = b.CD.as<double>();
+		a.CI = b.CI.as<int>(); a.Ht = b.Ht.as<double>(); a.Hx = b.Hx.as<double>();
+		a.histRecords = R; a.nprobes = 0; a.ngrid = 0; a.rawMaxPoints = 0;
+		a.remaining = b.remaining.as<int>();
+		a.attemptsPerLaunch = 1; a.stopBeforeSolve = 0;
+		if (simcuLaunchLoad(&a, 32, 0)) { fail("load kernel launch failed"); break; }
+		if (cudaDeviceSynchronize() != cudaSuccess) { fail("pilot load kernel failed"); break; }
+		if (needOP && analyseFrom(r, 0, b.A, P)) break;
+		if (needTran) {
+			if (r->sched[1].lu.empty()) r->sched[1].F = p.nnzA;
+			int tpb = 32, shared = 1;
+			if (genericShape(r, P, 32, &tpb, &shared, b.ws)) break;
+			a.lu = r->args[0].lu; a.luLen = r->args[0].luLen; a.xslot = r->args[0].xslot;
+			a.F = r->args[0].F; a.wsShared = shared; a.wsGlobal = b.ws.as<double>();
+			if (simcuLaunchOp(&a, tpb, 0, 0)) { fail("op kernel launch failed"); break; }
+			SimcuArgs t = a;
+			t.stopBeforeSolve = 1; t.F = 0; t.lu = nullptr; t.xslot = nullptr;
+			if (simcuLaunchTran(&t, tpb, 0)) { fail("tran kernel launch failed"); break; }
+			if (cudaDeviceSynchronize() != cudaSuccess) { fail("pilot kernels failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+			if (analyseFrom(r, 1, b.A, P)) break;
+		}
+		rc = 0;
+	} while (0);
+	DBuf *all[] = {&b.A, &b.B, &b.X, &b.S, &b.IS, &b.CD, &b.CI, &b.Ht, &b.Hx, &b.pinst, &b.iinst,
+		&b.remaining, &b.ws};
+	for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) all[i]->release();
+	return rc;
+}
+
+/* process-wide cache of compiled topologies, keyed by the generated source */
+std::map<std::string, std::shared_ptr<JitKernel> > gKernelCache;
+
+int buildJitKernel(simcu_ *r)
+{
+	if (r->jit && r->jitProbes == r->probeRows && r->jitTpb == r->tpb) return 0;
+	const std::string src = assembleSource(r->prog, r->sched, r->active, r->probeRows, r->tpb);
+	std::string key = src;
+	key += "//maxregs=" + std::to_string(r->maxRegs);
+	std::map<std::string, std::shared_ptr<JitKernel> >::iterator it = gKernelCache.find(key);
+	if (it != gKernelCache.end()) r->jit = it->second;
+	else {
+		std::shared_ptr<JitKernel> k(new JitKernel());
+		std::string err;
+		if (!jitCompile(src, r->maxRegs, *k, err)) return fail("%s", err.c_str());
+		if (!jitLoad(*k, r->tpb, err)) return fail("%s", err.c_str());
+		gKernelCache[key] = k;
+		r->jit = k;
+		r->stats.jitCompiles++;
+	}
+	r->jitProbes = r->probeRows; r->jitTpb = r->tpb;
+	return 0;
 }
 
 int resetState(simcu_ *r, cudaStream_t st)
@@ -670,36 +760,16 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		r->ngrid = ng;
 	}
 
-	/* program upload */
+	/* program upload (read by the generic kernels; tables and parameters by both) */
 	if (r->dDev.upload(p.dev) || r->dBvar.upload(p.bvar) || r->dCalcOff.upload(p.calcOff) ||
 			r->dCalcCode.upload(p.calcCode) || r->dCalcConst.upload(p.calcConst) ||
 			r->dCalcVarOff.upload(p.calcVarOff) || r->dCalcVars.upload(p.calcVars) ||
 			r->dHistRows.upload(p.histRows) || r->dProbeRows.upload(r->probeRows))
 		return -1;
-
-	/* T-line history ring length */
 	const int nh = (int)p.histRows.size();
-	int R = 0;
-	if (nh > 0 && !opOnly) {
-		R = r->histRecordsOpt;
-		if (R <= 0) {
-			size_t freeB = 0, totalB = 0;
-			CU(cudaMemGetInfo(&freeB, &totalB));
-			const double per = (double)(nh + 1) * 8.0 * M;
-			R = (int)std::min(4096.0, std::max(64.0, 0.25 * (double)totalB / per));
-		}
-	}
-	r->histRecords = R;
-
-	/* per-instance state */
 	const size_t m8 = (size_t)M * 8, m4 = (size_t)M * 4;
-	if (r->dA.reserve(p.nnzA * m8) || r->dB.reserve(p.N * m8) || r->dX.reserve(p.N * m8) ||
-			r->dS.reserve(std::max(1, p.stateDoubles) * m8) ||
-			r->dIS.reserve(std::max(1, p.stateInts) * m4) ||
-			r->dCD.reserve(CD_NUM * m8) || r->dCI.reserve(CI_NUM * m4) ||
-			r->dHt.reserve((size_t)R * m8) || r->dHx.reserve((size_t)R * nh * m8) ||
-			r->dOutGrid.reserve((size_t)r->ngrid * numProbes * m8) ||
-			r->dRemaining.reserve(sizeof(int)))
+	if (r->dCI.reserve(CI_NUM * m4) || r->dRemaining.reserve(2 * sizeof(int)) ||
+			r->dOutGrid.reserve((size_t)r->ngrid * numProbes * m8))
 		return -1;
 	if (r->rawMaxPoints > 0) {
 		if (r->rawCount < 1) { r->rawFirst = 0; r->rawCount = M; }
@@ -718,43 +788,72 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		a.calcOff = r->dCalcOff.as<int>(); a.calcCode = r->dCalcCode.as<int>();
 		a.calcConst = r->dCalcConst.as<double>();
 		a.calcVarOff = r->dCalcVarOff.as<int>(); a.calcVars = r->dCalcVars.as<int>();
-		a.histRows = r->dHistRows.as<int>(); a.nh = nh; a.histRecords = R;
+		a.histRows = r->dHistRows.as<int>(); a.nh = nh;
 		a.probeRows = r->dProbeRows.as<int>(); a.nprobes = numProbes; a.ngrid = r->ngrid;
 		a.rawMaxPoints = r->rawMaxPoints; a.rawFirst = r->rawFirst; a.rawCount = r->rawCount;
-		a.A = r->dA.as<double>(); a.B = r->dB.as<double>(); a.X = r->dX.as<double>();
-		a.Xrec = nullptr; a.S = r->dS.as<double>(); a.CD = r->dCD.as<double>();
-		a.IS = r->dIS.as<int>(); a.CI = r->dCI.as<int>();
-		a.Ht = r->dHt.as<double>(); a.Hx = r->dHx.as<double>();
+		a.CI = r->dCI.as<int>();
 		a.outGrid = r->dOutGrid.as<double>(); a.outRaw = r->dOutRaw.as<double>();
 		a.attemptsPerLaunch = r->attemptsPerLaunch;
 		a.maxAttempts = (r->maxAttempts > 0) ? r->maxAttempts : LLONG_MAX;
 		a.remaining = r->dRemaining.as<int>();
+		a.counter = r->dRemaining.as<int>() + 1;
 		a.stopBeforeSolve = 0;
 	}
 	if (uploadParameters(r, 0)) return -1;
+	if (uploadSchedule(r, 0) || uploadSchedule(r, 1)) return -1;
 
-	/* symbolic analysis on a pilot pass (one-off per topology and time scale) */
+	/* symbolic analysis on the pilot batch (one-off per topology and time scale) */
 	const bool needOP = r->sched[0].lu.empty() || !r->forcePc[0].empty();
 	const bool needTran = !opOnly && (r->sched[1].lu.empty() || runChanged || !r->forcePc[1].empty());
-	if (needOP || needTran) {
-		r->args[0].wsShared = 0; r->args[1].wsShared = 0;
-		if (resetState(r, 0)) return -1;
-		if (simcuLaunchLoad(&r->args[0], 64, 0)) return fail("load kernel launch failed");
-		if (needOP && analysePhase(r, 0)) return -1;
-		if (needTran) {
-			if (r->sched[1].lu.empty()) r->sched[1].F = p.nnzA;
-			if (chooseLaunchShape(r)) return -1;
-			if (simcuLaunchOp(&r->args[0], r->tpb, 0, 0)) return fail("op kernel launch failed");
-			SimcuArgs pilot = r->args[1];
-			pilot.stopBeforeSolve = 1; pilot.attemptsPerLaunch = 1;
-			pilot.F = 0; pilot.rawMaxPoints = 0; pilot.nprobes = 0;
-			if (simcuLaunchTran(&pilot, r->tpb, 0)) return fail("tran kernel launch failed");
-			CU(cudaDeviceSynchronize());
-			if (analysePhase(r, 1)) return -1;
+	if ((needOP || needTran) && pilotPass(r, needOP, needTran)) return -1;
+	if (opOnly && r->sched[1].lu.empty()) {
+		r->sched[1] = r->sched[0]; r->active[1] = r->active[0];
+		if (uploadSchedule(r, 1)) return -1;
+	}
+
+	int sms = 148, dev = 0;
+	CU(cudaGetDevice(&dev));
+	CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	int slots = M;
+	if (r->interpreter) {
+		/* whole batch on the generic kernels: per-instance state in HBM */
+		if (genericShape(r, M, r->tpbOpt, &r->tpb, &r->wsShared, r->dWs)) return -1;
+		if (r->dA.reserve(p.nnzA * m8) || r->dB.reserve(p.N * m8) || r->dX.reserve(p.N * m8) ||
+				r->dS.reserve(std::max(1, p.stateDoubles) * m8) ||
+				r->dIS.reserve(std::max(1, p.stateInts) * m4) || r->dCD.reserve(CD_NUM * m8))
+			return -1;
+	} else {
+		r->tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
+		r->wsShared = 0;
+		if (buildJitKernel(r)) return -1;
+		const int want = (M + r->tpb - 1) / r->tpb;
+		r->jitBlocks = std::max(1, std::min(want, sms * r->jit->maxBlocksPerSM));
+		slots = r->jitBlocks * r->tpb;
+	}
+
+	/* T-line history ring: one column per instance (interpreter) or per
+	 * resident thread (specialised kernel) */
+	int R = 0;
+	if (nh > 0 && !opOnly) {
+		R = r->histRecordsOpt;
+		if (R <= 0) {
+			size_t freeB = 0, totalB = 0;
+			CU(cudaMemGetInfo(&freeB, &totalB));
+			const double per = (double)(nh + 1) * 8.0 * slots;
+			R = (int)std::min(32768.0, std::max(64.0, 0.4 * (double)freeB / per));
 		}
 	}
-	if (opOnly && r->sched[1].lu.empty()) r->sched[1].F = r->sched[0].F;
-	if (chooseLaunchShape(r)) return -1;
+	r->histRecords = R;
+	if (r->dHt.reserve((size_t)R * slots * 8) || r->dHx.reserve((size_t)R * nh * slots * 8)) return -1;
+	for (int ph = 0; ph < 2; ph++) {
+		SimcuArgs &a = r->args[ph];
+		a.histRecords = R;
+		a.Ht = r->dHt.as<double>(); a.Hx = r->dHx.as<double>();
+		a.A = r->dA.as<double>(); a.B = r->dB.as<double>(); a.X = r->dX.as<double>();
+		a.Xrec = nullptr; a.S = r->dS.as<double>(); a.CD = r->dCD.as<double>();
+		a.IS = r->dIS.as<int>();
+		a.wsShared = r->wsShared; a.wsGlobal = r->dWs.as<double>();
+	}
 	CU(cudaDeviceSynchronize());
 	r->prepared = true;
 	return 0;
@@ -765,18 +864,29 @@ int runDevice(simcu_ *r, cudaStream_t st, bool opOnly)
 	if (!r || !r->prepared) return fail("simcuRunDevice before simcuPrepare");
 	int launches = 0;
 	CU(cudaEventRecord(r->ev0, st));
-	if (resetState(r, st)) return -1;
-	if (simcuLaunchLoad(&r->args[0], 128, st)) return fail("load kernel launch failed");
-	if (simcuLaunchOp(&r->args[0], r->tpb, opOnly ? 1 : 0, st)) return fail("op kernel launch failed");
-	launches += 2;
-	CU(cudaEventRecord(r->ev2, st));
-	while (!opOnly) {
-		CU(cudaMemsetAsync(r->dRemaining.p, 0, sizeof(int), st));
-		if (simcuLaunchTran(&r->args[1], r->tpb, st)) return fail("tran kernel launch failed");
-		launches++;
-		CU(cudaMemcpyAsync(r->hRemaining, r->dRemaining.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-		if (*r->hRemaining <= 0) break;
+	if (r->interpreter) {
+		if (resetState(r, st)) return -1;
+		if (simcuLaunchLoad(&r->args[0], 128, st)) return fail("load kernel launch failed");
+		if (simcuLaunchOp(&r->args[0], r->tpb, opOnly ? 1 : 0, st)) return fail("op kernel launch failed");
+		launches += 2;
+		CU(cudaEventRecord(r->ev2, st));
+		while (!opOnly) {
+			CU(cudaMemsetAsync(r->dRemaining.p, 0, sizeof(int), st));
+			if (simcuLaunchTran(&r->args[1], r->tpb, st)) return fail("tran kernel launch failed");
+			launches++;
+			CU(cudaMemcpyAsync(r->hRemaining, r->dRemaining.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+			CU(cudaStreamSynchronize(st));
+			if (*r->hRemaining <= 0) break;
+		}
+	} else {
+		CU(cudaMemsetAsync(r->dRemaining.p, 0, 2 * sizeof(int), st));
+		CU(cudaEventRecord(r->ev2, st));
+		int op = opOnly ? 1 : 0;
+		void *params[] = {(void *)&r->args[1], (void *)&op};
+		cudaError_t e = cudaLaunchKernel((const void *)r->jit->kernel, dim3(r->jitBlocks), dim3(r->tpb),
+				params, 0, st);
+		if (e != cudaSuccess) return fail("specialised kernel launch failed: %s", cudaGetErrorString(e));
+		launches = 1;
 	}
 	CU(cudaEventRecord(r->ev1, st));
 	CU(cudaStreamSynchronize(st));
@@ -812,6 +922,9 @@ int collectStats(simcu_ *r)
 	s.stateDoubles = p.stateDoubles;
 	s.histRows = (int)p.histRows.size(); s.histRecords = r->histRecords;
 	s.workspaceInShared = r->wsShared; s.threadsPerBlock = r->tpb;
+	s.registersPerThread = (r->jit && !r->interpreter) ? r->jit->numRegs : 0;
+	s.localBytesPerThread = (r->jit && !r->interpreter) ? (int)r->jit->localBytes : 0;
+	s.gridBlocks = r->interpreter ? (r->M + r->tpb - 1) / r->tpb : r->jitBlocks;
 	return 0;
 }
 
@@ -1011,6 +1124,47 @@ int simcuGetPivots(simcu_ *r, int phase, int *pc, int *pr)
 	if (!r || phase < 0 || phase > 1 || r->sched[phase].pc.empty()) return -1;
 	const Schedule &s = r->sched[phase];
 	for (size_t k = 0; k < s.pc.size(); k++) { pc[k] = s.pc[k]; pr[k] = s.pr[k]; }
+	return 0;
+}
+
+/* test hook: everything Prepare does short of touching a GPU - flatten, a
+ * structural symbolic analysis on random pilot values (or the forced pivots),
+ * source generation and the NVRTC compile for sm_100a */
+int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, int *cubinBytes)
+{
+	if (!r) return -1;
+	if (ensureCompiled(r)) return -1;
+	const Program &p = r->prog;
+	std::vector<int> probeRows;
+	for (int i = 0; i < numProbes; i++) {
+		const int row = r->nl.findRow(probes[i]);
+		if (row < 1) return fail("unknown probe %s", probes[i] ? probes[i] : "(null)");
+		probeRows.push_back(row);
+	}
+	Schedule sched[2];
+	std::vector<char> active[2] = {p.activeOP, p.activeTran};
+	unsigned long long seed = 0x9E3779B97F4A7C15ULL;
+	for (int ph = 0; ph < 2; ph++) {
+		std::vector<std::vector<double> > pilots(2, std::vector<double>(p.nnzA, 0.0));
+		for (size_t q = 0; q < pilots.size(); q++)
+			for (int sl = 0; sl < p.nnzA; sl++) {
+				seed = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+				if (active[ph][sl]) pilots[q][sl] = 0.5 + (double)(seed >> 40) / (double)(1 << 24);
+			}
+		const bool forced = (int)r->forcePc[ph].size() == p.N;
+		std::string err;
+		if (!analyse(p.N, p.colStart, p.rowIdx, active[ph], pilots, r->pivotThreshold,
+				forced ? r->forcePc[ph].data() : nullptr, forced ? r->forcePr[ph].data() : nullptr,
+				sched[ph], err))
+			return fail("%s", err.c_str());
+	}
+	const int tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
+	const std::string src = assembleSource(p, sched, active, probeRows, tpb);
+	if (source) *source = strdup(src.c_str());
+	JitKernel k;
+	std::string err;
+	if (!jitCompile(src, r->maxRegs, k, err)) return fail("%s", err.c_str());
+	if (cubinBytes) *cubinBytes = (int)k.cubin.size();
 	return 0;
 }
 

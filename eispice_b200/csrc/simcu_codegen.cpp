@@ -1,0 +1,386 @@
+/*
+ * simcu_codegen.cpp - writes the topology-specialised part of the production
+ * kernel: the netlist as literal device records fed to the hand-written device
+ * library (simcu_device.cuh), the B-source expressions as straight-line code
+ * (value and partial derivatives, same operations as the bytecode interpreter
+ * of simcu_calc.h / the reference's parser.lem actions), and the numeric LU +
+ * triangular solves of both phases fully unrolled on named scalars, so the
+ * factors live in registers and never touch memory.
+ *
+ * The text produced here is concatenated with simcu_program.h, simcu_calc.h,
+ * simcu_device.cuh and simcu_jit_kernel.cuh and compiled for sm_100a by NVRTC
+ * (simcu_jit.cpp).  Nothing in it depends on the number of instances, on
+ * parameter values or on the analysis window.
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/simulator_cuda.h"
+#include "simcu_codegen.h"
+
+namespace simcu {
+namespace {
+
+struct Out {
+	std::string s;
+	void f(const char *fmt, ...)
+	{
+		char buf[1024];
+		va_list ap;
+		va_start(ap, fmt);
+		const int n = std::vsnprintf(buf, sizeof buf, fmt, ap);
+		va_end(ap);
+		if (n >= (int)sizeof buf) {
+			std::vector<char> big(n + 1);
+			va_start(ap, fmt);
+			std::vsnprintf(big.data(), big.size(), fmt, ap);
+			va_end(ap);
+			s += big.data();
+		} else s += buf;
+	}
+};
+
+/* exact literal of a double (also inf / nan) */
+std::string lit(double v)
+{
+	unsigned long long bits;
+	std::memcpy(&bits, &v, sizeof bits);
+	char buf[64];
+	std::snprintf(buf, sizeof buf, "__longlong_as_double(0x%016llxLL)", bits);
+	return buf;
+}
+
+/* ---- B-source expressions -------------------------------------------------- */
+struct Dual { std::string f, d; };   /* d empty = structurally zero derivative */
+
+/* One evaluation of calc `id` as SSA statements: dvar < 0 value only, else the
+ * partial derivative against calc variable dvar.  Mirrors calcRun() of
+ * simcu_calc.h operation by operation; a derivative that is structurally zero
+ * (constants, other variables, comparison results) is dropped instead of being
+ * multiplied through, which differs from the interpreter only when an
+ * intermediate value is non-finite. */
+void emitCalc(Out &o, const Program &p, int id, int dvar, const char *ind)
+{
+	const int c0 = p.calcOff[id], c1 = p.calcOff[id + 1];
+	std::vector<Dual> st;
+	int t = 0;
+	auto tmp = [&](const std::string &expr) {
+		char name[32];
+		std::snprintf(name, sizeof name, "t%d", t++);
+		o.f("%sconst double %s = %s;\n", ind, name, expr.c_str());
+		return std::string(name);
+	};
+	for (int pc = c0; pc < c1; pc += 2) {
+		const int op = p.calcCode[pc], arg = p.calcCode[pc + 1];
+		switch (op) {
+		case OP_CONST: { Dual a; a.f = tmp(lit(p.calcConst[arg])); st.push_back(a); break; }
+		case OP_VAR: {
+			Dual a;
+			char nm[32];
+			std::snprintf(nm, sizeof nm, "v%d", arg);
+			a.f = nm;
+			if (arg == dvar) a.d = tmp("1.0");
+			st.push_back(a);
+			break;
+		}
+		case OP_NEG: {
+			Dual &b = st.back();
+			b.f = tmp("-1 * " + b.f);
+			if (!b.d.empty()) b.d = tmp("-1 * " + b.d);
+			break;
+		}
+		case OP_ADD: case OP_SUB: {
+			const Dual c = st.back(); st.pop_back();
+			Dual &b = st.back();
+			const char *sgn = (op == OP_ADD) ? " + " : " - ";
+			b.f = tmp(b.f + sgn + c.f);
+			if (!b.d.empty() && !c.d.empty()) b.d = tmp(b.d + sgn + c.d);
+			else if (!c.d.empty()) b.d = (op == OP_ADD) ? c.d : tmp("0.0 - " + c.d);
+			break;
+		}
+		case OP_MUL: {
+			const Dual c = st.back(); st.pop_back();
+			Dual &b = st.back();
+			std::string d;
+			if (!b.d.empty() && !c.d.empty()) d = tmp(b.d + " * " + c.f + " + " + b.f + " * " + c.d);
+			else if (!b.d.empty()) d = tmp(b.d + " * " + c.f);
+			else if (!c.d.empty()) d = tmp(b.f + " * " + c.d);
+			b.f = tmp(b.f + " * " + c.f);
+			b.d = d;
+			break;
+		}
+		case OP_DIV: {
+			const Dual c = st.back(); st.pop_back();
+			Dual &b = st.back();
+			std::string d;
+			if (!b.d.empty() || !c.d.empty()) {
+				std::string num;
+				if (!b.d.empty() && !c.d.empty()) num = b.d + " * " + c.f + " - " + b.f + " * " + c.d;
+				else if (!b.d.empty()) num = b.d + " * " + c.f;
+				else num = "0.0 - " + b.f + " * " + c.d;
+				d = tmp("calcDiv((" + num + "), (" + c.f + " * " + c.f + "), m)");
+			}
+			b.f = tmp("calcDiv(" + b.f + ", " + c.f + ", m)");
+			b.d = d;
+			break;
+		}
+		case OP_POW: {
+			const Dual c = st.back(); st.pop_back();
+			Dual &b = st.back();
+			const std::string pw = tmp("pow(" + b.f + ", " + c.f + ")");
+			std::string d;
+			if (!b.d.empty() || !c.d.empty()) {
+				const std::string left = b.d.empty() ? std::string()
+					: b.d + " * calcDiv(" + c.f + ", " + b.f + ", m)";
+				const std::string right = c.d.empty() ? std::string()
+					: "((" + b.f + " != 0.0) ? " + c.d + " * calcLn(" + b.f + ") : 0.0)";
+				if (!left.empty() && !right.empty()) d = tmp(pw + " * (" + left + " + " + right + ")");
+				else d = tmp(pw + " * (" + (left.empty() ? right : left) + ")");
+			}
+			b.f = pw;
+			b.d = d;
+			break;
+		}
+		case OP_FUNC: {
+			Dual &b = st.back();
+			char fn[32], dn[32];
+			std::snprintf(fn, sizeof fn, "t%d", t++);
+			std::snprintf(dn, sizeof dn, "t%d", t++);
+			o.f("%sdouble %s, %s; calcFunc(%d, %s, %s, m, &%s, &%s);\n", ind, fn, dn, arg,
+					b.f.c_str(), b.d.empty() ? "0.0" : b.d.c_str(), fn, dn);
+			/* u(x): the derivative 1/m at exactly 0 does not depend on x' */
+			const bool keep = !b.d.empty() || (arg == FN_U && dvar >= 0);
+			b.f = fn;
+			b.d = keep ? std::string(dn) : std::string();
+			break;
+		}
+		case OP_GT: case OP_LT: case OP_GE: case OP_LE: case OP_EQ: case OP_NE: {
+			const Dual c = st.back(); st.pop_back();
+			Dual &b = st.back();
+			const char *rel = (op == OP_GT) ? ">" : (op == OP_LT) ? "<" : (op == OP_GE) ? ">="
+				: (op == OP_LE) ? "<=" : (op == OP_EQ) ? "==" : "!=";
+			b.f = tmp("(" + b.f + " " + rel + " " + c.f + ") ? 1.0 : 0.0");
+			b.d.clear();
+			break;
+		}
+		case OP_NOT: {
+			Dual &b = st.back();
+			b.f = tmp("(" + b.f + " == 0.0) ? 1.0 : 0.0");
+			b.d.clear();
+			break;
+		}
+		case OP_AND: case OP_OR: {
+			const Dual c = st.back(); st.pop_back();
+			Dual &b = st.back();
+			b.f = tmp("((" + b.f + " == 1.0) " + ((op == OP_AND) ? "&&" : "||") + " (" + c.f +
+					" == 1.0)) ? 1.0 : 0.0");
+			b.d.clear();
+			break;
+		}
+		default: { /* OP_IF */
+			Dual &b = st.back();
+			b.f = tmp("(" + b.f + " != 0.0) ? 1.0 : 0.0");
+			b.d.clear();
+			break;
+		}
+		}
+	}
+	o.f("%sf = %s; dv = %s;\n", ind, st.back().f.c_str(),
+			(dvar >= 0 && !st.back().d.empty()) ? st.back().d.c_str() : "0.0");
+}
+
+void emitCalcAll(Out &o, const Program &p)
+{
+	o.f("DEV void genCalc(Inst &c, int id, int dvar, double &f, double &dv)\n{\n");
+	o.f("\tconst double m = c.a.ctl.gmin;\n\t(void)m;\n\tf = 0.0; dv = 0.0;\n\tswitch (id) {\n");
+	const int ncalc = (int)p.calcOff.size() - 1;
+	for (int id = 0; id < ncalc; id++) {
+		const int v0 = p.calcVarOff[id], v1 = p.calcVarOff[id + 1];
+		o.f("\tcase %d: {\n", id);
+		for (int k = v0; k < v1; k++) {
+			if (p.calcVars[k] == CALC_VAR_TIME) o.f("\t\tconst double v%d = c.time;\n", k - v0);
+			else o.f("\t\tconst double v%d = c.X(%d);\n", k - v0, p.calcVars[k]);
+		}
+		o.f("\t\tswitch (dvar) {\n");
+		for (int dv = -1; dv < v1 - v0; dv++) {
+			if (dv >= 0 && p.calcVars[v0 + dv] == CALC_VAR_TIME) continue;
+			o.f("\t\tcase %d: {\n", dv);
+			emitCalc(o, p, id, dv, "\t\t\t");
+			o.f("\t\t\tbreak;\n\t\t}\n");
+		}
+		o.f("\t\tdefault: break;\n\t\t}\n\t\tbreak;\n\t}\n");
+	}
+	o.f("\tdefault: break;\n\t}\n}\n\n");
+}
+
+/* ---- device phases ---------------------------------------------------------- */
+void emitRecord(Out &o, const Program &p, int k)
+{
+	const int *rec = &p.dev[(size_t)k * SIMCU_DEV_STRIDE];
+	o.f("\t{ const int d[] = {");
+	for (int j = 0; j < SIMCU_DEV_STRIDE; j++) o.f("%s%d", j ? "," : "", rec[j]);
+	o.f("};");
+	/* the Jacobian-variable table is a separate literal array: its loop bound
+	 * comes from d[], which must fold first */
+	const int kind = rec[DF_TYPE];
+	o.f(" const int bv[] = {");
+	if ((kind == DK_BI || kind == DK_BV || kind == DK_BC) && rec[DF_NBV] > 0) {
+		const int nbv = rec[DF_NBV], off = rec[DF_BVOFF];
+		for (int j = 0; j < 4 * nbv; j++) o.f("%s%d", j ? "," : "", p.bvar[(size_t)4 * off + j]);
+	} else o.f("0");
+	o.f("}; (void)bv;");
+}
+
+bool inPhase(const int *rec, int phase)
+{
+	const int kind = rec[DF_TYPE];
+	const bool wave = (kind == DK_V || kind == DK_I) && rec[DF_WTYPE] != 0;
+	const bool ta = (kind == DK_VI) && rec[DF_TATAB] >= 0;
+	const bool bsrc = (kind == DK_BI || kind == DK_BV || kind == DK_BC);
+	switch (phase) {
+	case 0: return true;                                                /* load */
+	case 1: return kind == DK_C || kind == DK_L || kind == DK_BC || kind == DK_T;   /* initStep */
+	case 2: return wave || ta || kind == DK_T || (bsrc && rec[DF_USETIME]);          /* step */
+	case 3: return kind == DK_C || kind == DK_L || kind == DK_BC;                   /* integrate */
+	case 4: return kind == DK_VI || bsrc;                                            /* linearize */
+	case 5: return kind == DK_C || kind == DK_L || kind == DK_BC;                   /* minStep */
+	default: return wave || ta;                                                      /* nextStep */
+	}
+}
+
+void emitPhases(Out &o, const Program &p)
+{
+	static const char *const head[7] = {
+		"DEV void genLoad(Inst &c)\n{\n",
+		"DEV void genInitStep(Inst &c)\n{\n",
+		"DEV int genStep(Inst &c)\n{\n\tint brk = 0;\n",
+		"DEV void genIntegrate(Inst &c)\n{\n",
+		"DEV int genLinearize(Inst &c)\n{\n\tint linear = 1;\n",
+		"DEV void genMinStep(Inst &c, double &lteStep)\n{\n",
+		"DEV void genNextStep(Inst &c, double &thisStep)\n{\n"};
+	static const char *const call[7] = {
+		" devLoad(c, d, bv); }\n", " devInitStep(c, d); }\n", " brk |= devStep(c, d, bv); }\n",
+		" devIntegrate(c, d); }\n", " linear &= devLinearize(c, d, bv); }\n",
+		" devMinStep(c, d, lteStep); }\n", " devNextStep(c, d, thisStep); }\n"};
+	static const char *const onErr[7] = {
+		"\tif (c.err) return;\n", "", "\tif (c.err) return brk;\n", "\tif (c.err) return;\n",
+		"\tif (c.err) return 0;\n", "\tif (c.err) return;\n", ""};
+	static const char *const tail[7] = {"}\n\n", "}\n\n", "\treturn brk;\n}\n\n", "}\n\n",
+		"\treturn linear;\n}\n\n", "}\n\n", "}\n\n"};
+	for (int ph = 0; ph < 7; ph++) {
+		o.f("%s", head[ph]);
+		for (int k = 0; k < p.ndev; k++) {
+			if (!inPhase(&p.dev[(size_t)k * SIMCU_DEV_STRIDE], ph)) continue;
+			emitRecord(o, p, k);
+			o.f("%s%s", call[ph], onErr[ph]);
+		}
+		o.f("%s", tail[ph]);
+	}
+}
+
+/* ---- numeric LU + solves, straight-line --------------------------------------- */
+void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vector<char> &active,
+		int phase)
+{
+	const int N = p.N, F = s.F;
+	o.f("/* %s: %d unknowns, %d matrix slots (%d fill), %d L + %d U off-diagonal entries */\n",
+			phase ? "transient" : "operating point", N, F, F - p.nnzA, s.nL, s.nU);
+	o.f("DEV void genFactorSolve%d(Inst &c)\n{\n\tbool bad = false;\n", phase);
+	/* which slots the schedule touches */
+	std::vector<char> used(F, 0);
+	{
+		int pos = 0;
+		for (int k = 0; k < N; k++) {
+			const int nU = s.lu[pos + 2], nL = s.lu[pos + 3];
+			used[s.lu[pos]] = 1;
+			for (int j = 0; j < nU; j++) used[s.lu[pos + 4 + 2 * j]] = 1;
+			const int *lrow = &s.lu[pos + 4 + 2 * nU];
+			for (int r = 0; r < nL; r++) {
+				const int *e = lrow + r * (2 + nU);
+				used[e[0]] = 1;
+				for (int j = 0; j < nU; j++) used[e[2 + j]] = 1;
+			}
+			pos += 4 + 2 * nU + nL * (2 + nU);
+		}
+	}
+	for (int sl = 0; sl < F; sl++) {
+		if (!used[sl]) continue;
+		if (sl < p.nnzA && active[sl]) o.f("\tdouble w%d = c.Av[%d];\n", sl, sl);
+		else o.f("\tdouble w%d = 0.0;\n", sl);
+	}
+	for (int r = 0; r < N; r++) o.f("\tdouble y%d = c.Bv[%d];\n", r, r);
+	int pos = 0;
+	std::vector<int> start(N);
+	for (int k = 0; k < N; k++) {
+		start[k] = pos;
+		const int d = s.lu[pos], yk = s.lu[pos + 1] - F, nU = s.lu[pos + 2], nL = s.lu[pos + 3];
+		const int *u = &s.lu[pos + 4];
+		const int *lrow = u + 2 * nU;
+		o.f("\tconst double i%d = 1.0 / w%d; bad |= (w%d == 0.0) | !isfinite(i%d);\n", k, d, d, k);
+		for (int r = 0; r < nL; r++) {
+			const int *e = lrow + r * (2 + nU);
+			o.f("\t{ const double l = w%d * i%d;", e[0], k);
+			for (int j = 0; j < nU; j++) o.f(" w%d -= l * w%d;", e[2 + j], u[2 * j]);
+			o.f(" y%d -= l * y%d; }\n", e[1] - F, yk);
+		}
+		pos += 4 + 2 * nU + nL * (2 + nU);
+	}
+	/* back substitution, reverse pivot order; the solution of column pc[k]
+	 * replaces the right-hand side of its pivot row */
+	for (int k = N - 1; k >= 0; k--) {
+		const int q = start[k];
+		const int yk = s.lu[q + 1] - F, nU = s.lu[q + 2];
+		const int *u = &s.lu[q + 4];
+		o.f("\t{ double acc = y%d;", yk);
+		for (int j = 0; j < nU; j++) o.f(" acc -= w%d * y%d;", u[2 * j], u[2 * j + 1] - F);
+		o.f(" y%d = acc * i%d; }\n", yk, k);
+	}
+	for (int col = 0; col < N; col++) o.f("\tc.Xv[%d] = y%d;\n", col, s.xslot[col] - F);
+	o.f("\tif (bad) c.err = SIMCU_ERR_SINGULAR;\n}\n\n");
+}
+
+void emitRows(Out &o, const char *name, const std::vector<int> &rows)
+{
+	o.f("DEV void %s(int *rows)\n{\n", name);
+	for (size_t j = 0; j < rows.size(); j++) o.f("\trows[%zu] = %d;\n", j, rows[j]);
+	o.f("\t(void)rows;\n}\n\n");
+}
+
+}  /* namespace */
+
+std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock)
+{
+	Out o;
+	o.f("#define SIMCU_JIT 1\n");
+	o.f("#define SIMCU_N %d\n#define SIMCU_NNZ %d\n#define SIMCU_SD %d\n#define SIMCU_SI %d\n",
+			p.N, p.nnzA, p.stateDoubles, p.stateInts);
+	o.f("#define SIMCU_NPARAM %d\n#define SIMCU_NISET %d\n#define SIMCU_NH %d\n",
+			(int)p.pmap.size(), p.niinst, (int)p.histRows.size());
+	o.f("#define SIMCU_NPROBES %d\n#define SIMCU_TPB %d\n", numProbes, threadsPerBlock);
+	o.f("#define HUGE_VAL (__longlong_as_double(0x7ff0000000000000LL))\n");
+	o.f("#define M_PI 3.14159265358979323846\n");
+	o.f("enum { SIMCU_OK = %d, SIMCU_ERR_TIMESTEP = %d, SIMCU_ERR_SINGULAR = %d, SIMCU_ERR_NAN = %d,\n"
+			"\tSIMCU_ERR_OP = %d, SIMCU_ERR_HISTORY = %d, SIMCU_ERR_BUDGET = %d };\n\n",
+			SIMCU_OK, SIMCU_ERR_TIMESTEP, SIMCU_ERR_SINGULAR, SIMCU_ERR_NAN, SIMCU_ERR_OP,
+			SIMCU_ERR_HISTORY, SIMCU_ERR_BUDGET);
+	return o.s;
+}
+
+std::string generateTopology(const Program &p, const Schedule sched[2],
+		const std::vector<char> active[2], const std::vector<int> &probeRows)
+{
+	Out o;
+	o.f("/* ---- generated for this netlist by simcu_codegen.cpp ---- */\n");
+	emitCalcAll(o, p);
+	emitPhases(o, p);
+	emitFactorSolve(o, p, sched[0], active[0], 0);
+	emitFactorSolve(o, p, sched[1], active[1], 1);
+	emitRows(o, "genHistRows", p.histRows);
+	emitRows(o, "genProbeRows", probeRows);
+	return o.s;
+}
+
+}  /* namespace simcu */

@@ -1,0 +1,44 @@
+/*
+ * simcu_codegen.h - source generation for the topology-specialised kernel
+ * (simcu_codegen.cpp) and its NVRTC compilation / loading (simcu_jit.cpp).
+ */
+#ifndef SIMCU_CODEGEN_H
+#define SIMCU_CODEGEN_H
+
+#include <string>
+#include <vector>
+
+#include "simcu_host.h"
+
+namespace simcu {
+
+/* #defines of the topology's sizes; first part of the translation unit */
+std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock);
+/* device records, expressions and the unrolled LU of both phases */
+std::string generateTopology(const Program &p, const Schedule sched[2],
+		const std::vector<char> active[2], const std::vector<int> &probeRows);
+/* prelude + embedded library headers + topology + kernel */
+std::string assembleSource(const Program &p, const Schedule sched[2],
+		const std::vector<char> active[2], const std::vector<int> &probeRows,
+		int threadsPerBlock);
+
+/* A compiled kernel.  compile() needs no GPU (NVRTC only); load() does. */
+struct JitKernel {
+	std::vector<char> cubin;
+	std::string log;
+	void *library = nullptr;      /* cudaLibrary_t */
+	void *kernel = nullptr;       /* cudaKernel_t */
+	int numRegs = 0;
+	size_t localBytes = 0;
+	int maxBlocksPerSM = 0;
+	~JitKernel();
+};
+/* maxRegs = 0: let ptxas choose.  Returns false and fills err on failure. */
+bool jitCompile(const std::string &source, int maxRegs, JitKernel &k, std::string &err);
+bool jitLoad(JitKernel &k, int threadsPerBlock, std::string &err);
+/* where libnvrtc was found ("" before the first compile) */
+const char *jitNvrtcPath();
+void jitSetNvrtcPath(const char *path);
+
+}  /* namespace simcu */
+#endif

@@ -1,0 +1,156 @@
+/*
+ * simcu_jit.cpp - compiles the topology-specialised translation unit with
+ * NVRTC for sm_100a and loads the cubin through the CUDA runtime's library API.
+ * libnvrtc is opened with dlopen at the first compile, so libsimulator_cuda.so
+ * itself links against nothing but the (static) CUDA runtime and loads on a
+ * machine without a driver; compiling needs no GPU either, loading does.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "simcu_codegen.h"
+
+namespace simcu {
+
+namespace {
+
+/* simcu_program.h, simcu_calc.h, simcu_device.cuh, simcu_jit_kernel.cuh as raw
+ * string literals (written by the Makefile, #include lines removed) */
+#include "simcu_embed.inc"
+
+struct Nvrtc {
+	void *handle = nullptr;
+	std::string path;
+	decltype(&nvrtcCreateProgram) createProgram = nullptr;
+	decltype(&nvrtcCompileProgram) compileProgram = nullptr;
+	decltype(&nvrtcDestroyProgram) destroyProgram = nullptr;
+	decltype(&nvrtcGetProgramLogSize) getLogSize = nullptr;
+	decltype(&nvrtcGetProgramLog) getLog = nullptr;
+	decltype(&nvrtcGetCUBINSize) getCubinSize = nullptr;
+	decltype(&nvrtcGetCUBIN) getCubin = nullptr;
+	decltype(&nvrtcGetErrorString) errorString = nullptr;
+};
+Nvrtc gNvrtc;
+std::string gNvrtcHint;
+
+bool openNvrtc(std::string &err)
+{
+	if (gNvrtc.handle) return true;
+	std::vector<std::string> names;
+	if (!gNvrtcHint.empty()) names.push_back(gNvrtcHint);
+	if (const char *e = std::getenv("SIMCU_NVRTC")) names.push_back(e);
+	names.push_back("libnvrtc.so.12");
+	names.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+	names.push_back("/usr/local/cuda/lib64/libnvrtc.so");
+	names.push_back("libnvrtc.so");
+	for (size_t i = 0; i < names.size() && !gNvrtc.handle; i++) {
+		gNvrtc.handle = dlopen(names[i].c_str(), RTLD_NOW | RTLD_LOCAL);
+		if (gNvrtc.handle) gNvrtc.path = names[i];
+	}
+	if (!gNvrtc.handle) { err = "cannot load libnvrtc (set SIMCU_NVRTC to its path)"; return false; }
+#define SYM(member, name) \
+	gNvrtc.member = (decltype(gNvrtc.member))dlsym(gNvrtc.handle, name); \
+	if (!gNvrtc.member) { err = std::string("libnvrtc lacks ") + name; return false; }
+	SYM(createProgram, "nvrtcCreateProgram")
+	SYM(compileProgram, "nvrtcCompileProgram")
+	SYM(destroyProgram, "nvrtcDestroyProgram")
+	SYM(getLogSize, "nvrtcGetProgramLogSize")
+	SYM(getLog, "nvrtcGetProgramLog")
+	SYM(getCubinSize, "nvrtcGetCUBINSize")
+	SYM(getCubin, "nvrtcGetCUBIN")
+	SYM(errorString, "nvrtcGetErrorString")
+#undef SYM
+	return true;
+}
+
+}  /* namespace */
+
+const char *jitNvrtcPath() { return gNvrtc.path.c_str(); }
+void jitSetNvrtcPath(const char *path) { gNvrtcHint = path ? path : ""; }
+
+std::string assembleSource(const Program &p, const Schedule sched[2],
+		const std::vector<char> active[2], const std::vector<int> &probeRows,
+		int threadsPerBlock)
+{
+	std::string s = generatePrelude(p, (int)probeRows.size(), threadsPerBlock);
+	s += kSrcProgram;
+	s += kSrcCalc;
+	s += kSrcDevice;
+	s += generateTopology(p, sched, active, probeRows);
+	s += kSrcJitKernel;
+	return s;
+}
+
+JitKernel::~JitKernel()
+{
+	if (library) cudaLibraryUnload((cudaLibrary_t)library);
+}
+
+bool jitCompile(const std::string &source, int maxRegs, JitKernel &k, std::string &err)
+{
+	if (!openNvrtc(err)) return false;
+	nvrtcProgram prog = nullptr;
+	nvrtcResult rc = gNvrtc.createProgram(&prog, source.c_str(), "simcu_topology.cu", 0, nullptr, nullptr);
+	if (rc != NVRTC_SUCCESS) { err = gNvrtc.errorString(rc); return false; }
+	char regs[64];
+	std::snprintf(regs, sizeof regs, "--maxrregcount=%d", maxRegs);
+	std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
+		"--fmad=true", "-default-device"};
+	opts.pop_back();
+	if (maxRegs > 0) opts.push_back(regs);
+	rc = gNvrtc.compileProgram(prog, (int)opts.size(), opts.data());
+	size_t logSize = 0;
+	gNvrtc.getLogSize(prog, &logSize);
+	if (logSize > 1) {
+		k.log.resize(logSize);
+		gNvrtc.getLog(prog, &k.log[0]);
+	}
+	if (rc != NVRTC_SUCCESS) {
+		err = std::string("NVRTC: ") + gNvrtc.errorString(rc) + "\n" + k.log;
+		gNvrtc.destroyProgram(&prog);
+		return false;
+	}
+	size_t n = 0;
+	gNvrtc.getCubinSize(prog, &n);
+	k.cubin.resize(n);
+	gNvrtc.getCubin(prog, k.cubin.data());
+	gNvrtc.destroyProgram(&prog);
+	return true;
+}
+
+bool jitLoad(JitKernel &k, int threadsPerBlock, std::string &err)
+{
+	cudaLibrary_t lib = nullptr;
+	cudaError_t e = cudaLibraryLoadData(&lib, k.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+	if (e != cudaSuccess) { err = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e); return false; }
+	k.library = lib;
+	cudaKernel_t kern = nullptr;
+	e = cudaLibraryGetKernel(&kern, lib, "simcuJitKernel");
+	if (e != cudaSuccess) { err = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e); return false; }
+	k.kernel = kern;
+	cudaFuncAttributes attr;
+	if (cudaFuncGetAttributes(&attr, (const void *)kern) == cudaSuccess) {
+		k.numRegs = attr.numRegs;
+		k.localBytes = attr.localSizeBytes;
+	} else cudaGetLastError();
+	int blocks = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, (const void *)kern, threadsPerBlock, 0)
+			== cudaSuccess && blocks > 0) {
+		k.maxBlocksPerSM = blocks;
+	} else {
+		cudaGetLastError();
+		const int regs = k.numRegs > 0 ? k.numRegs : 255;
+		const int perBlock = ((regs * 32 + 255) / 256 * 256) * (threadsPerBlock / 32);
+		k.maxBlocksPerSM = std::max(1, std::min(32, 65536 / std::max(1, perBlock)));
+	}
+	return true;
+}
+
+}  /* namespace simcu */

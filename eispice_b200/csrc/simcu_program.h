@@ -143,6 +143,7 @@ typedef struct {
 	long long maxAttempts;
 	int *remaining;           /* device counter of unfinished instances */
 	int stopBeforeSolve;      /* pilot: assemble the first attempt, then stop */
+	int *counter;             /* specialised kernel: next unclaimed instance */
 } SimcuArgs;
 
 #endif

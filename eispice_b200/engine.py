@@ -37,7 +37,9 @@ class Stats(C.Structure):
                 ("stateDoubles", C.c_int), ("histRows", C.c_int),
                 ("histRecords", C.c_int), ("workspaceInShared", C.c_int),
                 ("threadsPerBlock", C.c_int), ("kernelLaunches", C.c_int),
-                ("deviceMs", C.c_double), ("tranMs", C.c_double)]
+                ("deviceMs", C.c_double), ("tranMs", C.c_double),
+                ("jitCompiles", C.c_int), ("registersPerThread", C.c_int),
+                ("localBytesPerThread", C.c_int), ("gridBlocks", C.c_int)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -100,6 +102,7 @@ def lib():
     L.simcuSymbolic.argtypes = [C.c_int, vp, vp, C.c_int, vp, C.c_double, vp, vp, ip, ip]
     L.simcuCalcEval.argtypes = [cp, C.c_int, vp, vp, C.c_double, C.c_int, dp, vp]
     L.simcuFree.argtypes = [vp]
+    L.simcuCompileOnly.argtypes = [vp, vp, C.c_int, vp, ip]
     L.simcuSetDevice.argtypes = [C.c_int]
     _lib = L
     return L
@@ -381,6 +384,18 @@ class Engine:
         data, status = self.fetch()
         return BatchResult(data, output_grid(tstep, tstop, self.ngrid), status,
                            self.stats(), probes)
+
+    def compile_only(self, probes=()):
+        """(source text, cubin bytes) of the topology-specialised kernel; needs
+        NVRTC but no GPU."""
+        src = C.c_char_p()
+        n = C.c_int()
+        rc = self.L.simcuCompileOnly(self.h, self._probe_array(probes), len(probes),
+                                     C.byref(src), C.byref(n))
+        text = src.value.decode() if src.value else ""
+        if rc != 0:
+            raise RuntimeError("simcuCompileOnly failed")
+        return text, n.value
 
     def close(self):
         if getattr(self, "h", None):

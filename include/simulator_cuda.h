@@ -62,6 +62,10 @@ typedef struct {
 	int kernelLaunches;        /* launches of the last simcuRunDevice */
 	double deviceMs;           /* device time of the last simcuRunDevice */
 	double tranMs;             /* of which: the transient kernel launches */
+	int jitCompiles;           /* NVRTC compilations this handle caused */
+	int registersPerThread;    /* of the topology-specialised kernel */
+	int localBytesPerThread;
+	int gridBlocks;
 } simcuStats_;
 
 /* simulatorNew (simulator.h:33): r must be NULL */
@@ -123,7 +127,10 @@ int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
 /* Options: reltol vntol abstol captol chgtol trtol gmin itl1 itl4 maxorder
  * minstep (control.h:34-56); hist_records, max_attempts, attempts_per_launch,
  * threads_per_block, workspace_shared (0/1), raw_max_points, raw_first,
- * raw_count, pivot_threshold, num_pilots; r = NULL: quiet (0/1) */
+ * raw_count, pivot_threshold, num_pilots, max_registers (of the specialised
+ * kernel, 0 = compiler's choice), interpreter (1: run the batch on the generic
+ * table-driven kernels instead of the NVRTC-specialised one; for verification);
+ * r = NULL: quiet (0/1) */
 int simcuSetOption(simcu_ *r, char *name, double value);
 /* Force the pivot sequence of a phase (0 = operating point, 1 = transient)
  * instead of the built-in pilot analysis: step k eliminates column pc[k] with
@@ -188,6 +195,11 @@ const char *simcuVariableName(simcu_ *r, int k);
 /* fixed pivot sequence chosen by Prepare: phase 0 = operating point,
  * 1 = transient; step k eliminates column pc[k] with pivot row pr[k] */
 int simcuGetPivots(simcu_ *r, int phase, int *pc, int *pr);
+/* test hook (no GPU needed): flatten, structural symbolic analysis, source
+ * generation and NVRTC compilation of the topology-specialised kernel.
+ * *source (optional) receives the malloc'd translation unit. */
+int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source,
+		int *cubinBytes);
 /* test hook: the symbolic analysis alone.  CSC pattern + numPilots value sets
  * ([numPilots][nnz]) in, pivot sequence, workspace slots and nnz(L+U-I) out */
 int simcuSymbolic(int n, const int *colStart, const int *rowIdx, int numPilots,

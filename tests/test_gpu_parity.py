@@ -240,3 +240,32 @@ def test_full_size_properties_cfg2():
     assert np.array_equal(r2.data, res.data[pick])
     small.close()
     eng.close()
+
+
+@pytest.mark.parametrize("cfg,M", [("cfg2", 48), ("cfg3", 40), ("cfg4", 24)])
+def test_specialised_kernel_equals_generic_kernels(cfg, M):
+    """The NVRTC-specialised production kernel and the table-driven generic
+    kernels (used for the pilot pass) run the same device library with the same
+    pivot sequence: same accepted-step sequences, values inside the tight gate."""
+    w = workloads.make(cfg, M)
+    jit = engine.Engine(w.cct.netlist(), w.M)
+    a = jit.tran_batch(w.tstep, w.tstop, 0.0, w.params, w.probes, raw_max_points=12000,
+                       raw_count=w.M)
+    assert a.stats["registersPerThread"] > 0 and a.stats["kernelLaunches"] == 1
+    gen = engine.Engine(w.cct.netlist(), w.M)
+    for ph in (0, 1):
+        gen.set_pivots(ph, *jit.pivots(ph))
+    b = gen.tran_batch(w.tstep, w.tstop, 0.0, w.params, w.probes, raw_max_points=12000,
+                       raw_count=w.M, interpreter=1)
+    assert b.stats["registersPerThread"] == 0 and b.stats["kernelLaunches"] >= 3
+    assert (a.status == 0).all() and (b.status == 0).all()
+    same = 0
+    for i in range(w.M):
+        ra = parity.drop_degenerate(jit.fetch_raw(i), w.tstep)
+        rb = parity.drop_degenerate(gen.fetch_raw(i), w.tstep)
+        if ra.shape == rb.shape:
+            frac, worst = parity.tight_fraction(ra, rb)
+            same += frac >= MIN_TIGHT_FRACTION
+    assert same >= 0.9 * w.M, "%d of %d instances share the step sequence" % (same, w.M)
+    jit.close()
+    gen.close()

@@ -276,3 +276,34 @@ def test_runs_fail_loudly_without_a_gpu():
             cct.tran_batch('0.01n', '10n', probes=["v(out)"])
     finally:
         L.simcuSetOption(None, b"quiet", 0.0)
+
+
+# ---- topology-specialised kernel: generation + NVRTC, no GPU needed ---------
+@pytest.mark.parametrize("name", ["cfg1_rc", "cfg2_rectifier", "cfg3_oscillator", "tline_lossy",
+                                  "b_capacitor", "b_voltage_time", "w_pwc", "w_gauss", "realc",
+                                  "vi_table", "cccs", "cfg4_ibis"])
+def test_specialised_kernel_compiles_for_sm100a(name):
+    build, an, _ = circuits.all_cases()[name]
+    eng = engine.Engine(build().netlist(), 1)
+    names = eng.variables()
+    src, cubin_bytes = eng.compile_only(names[1:3])
+    assert cubin_bytes > 10000
+    assert "simcuJitKernel" in src and "genFactorSolve1" in src
+    # every device of the netlist appears in the load phase, in insertion order
+    load = src[src.index("DEV void genLoad"):src.index("DEV void genInitStep")]
+    assert load.count("devLoad(c, d, bv)") == len(build().netlist())
+    eng.close()
+
+
+def test_specialised_source_is_independent_of_instances_and_values():
+    """One compilation serves every batch size and parameter value."""
+    import workloads
+    w1 = workloads.make("cfg2", 16)
+    w2 = workloads.make("cfg2", 48, seed_offset=3)
+    srcs = []
+    for w in (w1, w2):
+        eng = engine.Engine(w.cct.netlist(), w.M)
+        eng.set_params(w.params)
+        srcs.append(eng.compile_only(w.probes)[0])
+        eng.close()
+    assert srcs[0] == srcs[1]
