@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tpb", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--maxregs", type=int, default=0)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
@@ -218,6 +220,10 @@ def main():
     eng = engine.Engine(w.cct.netlist(), w.M)
     if a.tpb:
         eng.set_option("threads_per_block", a.tpb)
+    if a.lanes:
+        eng.set_option("lanes_per_warp", a.lanes)
+    if a.maxregs:
+        eng.set_option("max_registers", a.maxregs)
     eng.set_params(w.params)
     t0 = time.perf_counter()
     eng.prepare(w.tstep, w.tstop, 0.0, w.probes)
@@ -314,7 +320,9 @@ def main():
                        "solves_per_timestep": round(k, 3),
                        "timesteps_per_instance": round(accepted / a.steps / w.M, 1),
                        "threads_per_block": st["threadsPerBlock"],
-                       "lu_workspace": "shared" if st["workspaceInShared"] else "global",
+                       "grid_blocks": st["gridBlocks"], "lanes_per_warp": st["lanesPerWarp"],
+                       "registers_per_thread": st["registersPerThread"],
+                       "local_bytes_per_thread": st["localBytesPerThread"],
                        "l2": "flushed between timed steps (256 MiB write)",
                        "failed_instances": int(failed_all),
                        "prepare_s": round(prepare_s, 3)},
@@ -323,7 +331,7 @@ def main():
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "simcuTranKernel",
+                         "kernel": "simcuJitKernel",
                          "bytes_per_instance_timestep": round(balg, 1),
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             "clocks": clocks,

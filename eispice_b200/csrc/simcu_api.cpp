@@ -105,7 +105,7 @@ struct _simcu {
 	std::vector<char> active[2];
 	std::shared_ptr<JitKernel> jit;
 	std::vector<int> jitProbes;
-	int jitTpb = 0, jitBlocks = 0;
+	int jitTpb = 0, jitBlocks = 0, lanes = 32, lanesOpt = 0;
 	SimcuArgs args[2];
 	simcuStats_ stats;
 	/* device memory */
@@ -495,6 +495,7 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "pivot_threshold") { r->pivotThreshold = value; r->sched[0].lu.clear(); r->sched[1].lu.clear(); }
 	else if (n == "num_pilots") r->numPilots = std::max(1, (int)value);
 	else if (n == "interpreter") r->interpreter = (value != 0.0);
+	else if (n == "lanes_per_warp") r->lanesOpt = (int)value;
 	else if (n == "max_registers") { r->maxRegs = (int)value; r->jit.reset(); }
 	else return fail("unknown option %s", name);
 	r->prepared = false;
@@ -826,9 +827,21 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		r->tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
 		r->wsShared = 0;
 		if (buildJitKernel(r)) return -1;
-		const int want = (M + r->tpb - 1) / r->tpb;
-		r->jitBlocks = std::max(1, std::min(want, sms * r->jit->maxBlocksPerSM));
-		slots = r->jitBlocks * r->tpb;
+		/* active lanes per warp: the fewest (power of two) that still keep
+		 * the whole batch resident at once */
+		const int wpb = r->tpb / 32;
+		const long long capacity = (long long)sms * r->jit->maxBlocksPerSM * wpb;
+		int lanes = 32;
+		if (r->lanesOpt > 0) lanes = std::min(32, std::max(1, r->lanesOpt));
+		else while (lanes > 1 && ((long long)M + lanes / 2 - 1) / (lanes / 2) <= capacity) lanes /= 2;
+		int pow2 = 1;
+		while (pow2 * 2 <= lanes) pow2 *= 2;
+		r->lanes = pow2;
+		const long long warps = ((long long)M + r->lanes - 1) / r->lanes;
+		const long long want = (warps + wpb - 1) / wpb;
+		r->jitBlocks = (int)std::max(1LL, std::min(want, capacity / wpb));
+		slots = r->jitBlocks * wpb * r->lanes;
+		r->args[0].lanes = r->args[1].lanes = r->lanes;
 	}
 
 	/* T-line history ring: one column per instance (interpreter) or per
@@ -925,6 +938,7 @@ int collectStats(simcu_ *r)
 	s.registersPerThread = (r->jit && !r->interpreter) ? r->jit->numRegs : 0;
 	s.localBytesPerThread = (r->jit && !r->interpreter) ? (int)r->jit->localBytes : 0;
 	s.gridBlocks = r->interpreter ? (r->M + r->tpb - 1) / r->tpb : r->jitBlocks;
+	s.lanesPerWarp = r->interpreter ? 32 : r->lanes;
 	return 0;
 }
 

@@ -147,15 +147,19 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 
 extern "C" __global__ void __launch_bounds__(SIMCU_TPB) simcuJitKernel(const SimcuArgs a, int opOnly)
 {
+	/* a.lanes < 32 spreads a batch that is too small to fill the machine over
+	 * more warps (fewer instances per warp): the kernel is latency-bound, so
+	 * idle schedulers cost more than idle lanes, and divergence shrinks too */
 	const int lane = threadIdx.x & 31;
-	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-	const size_t hstride = (size_t)gridDim.x * blockDim.x;
+	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int slot = warp * a.lanes + lane;
+	const size_t hstride = (size_t)((gridDim.x * blockDim.x) >> 5) * a.lanes;
 	for (;;) {
 		int base = 0;
-		if (lane == 0) base = atomicAdd(a.counter, 32);
+		if (lane == 0) base = atomicAdd(a.counter, a.lanes);
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= a.M) break;
-		if (base + lane < a.M) jitRunInstance(a, base + lane, slot, hstride, opOnly);
+		if (lane < a.lanes && base + lane < a.M) jitRunInstance(a, base + lane, slot, hstride, opOnly);
 		__syncwarp();
 	}
 }

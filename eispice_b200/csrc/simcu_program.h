@@ -144,6 +144,7 @@ typedef struct {
 	int *remaining;           /* device counter of unfinished instances */
 	int stopBeforeSolve;      /* pilot: assemble the first attempt, then stop */
 	int *counter;             /* specialised kernel: next unclaimed instance */
+	int lanes;                /* active lanes per warp (power of two <= 32) */
 } SimcuArgs;
 
 #endif

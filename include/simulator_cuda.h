@@ -66,6 +66,7 @@ typedef struct {
 	int registersPerThread;    /* of the topology-specialised kernel */
 	int localBytesPerThread;
 	int gridBlocks;
+	int lanesPerWarp;          /* instances per warp of the specialised kernel */
 } simcuStats_;
 
 /* simulatorNew (simulator.h:33): r must be NULL */
@@ -128,7 +129,7 @@ int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
  * minstep (control.h:34-56); hist_records, max_attempts, attempts_per_launch,
  * threads_per_block, workspace_shared (0/1), raw_max_points, raw_first,
  * raw_count, pivot_threshold, num_pilots, max_registers (of the specialised
- * kernel, 0 = compiler's choice), interpreter (1: run the batch on the generic
+ * kernel, 0 = compiler's choice), lanes_per_warp (0 = automatic), interpreter (1: run the batch on the generic
  * table-driven kernels instead of the NVRTC-specialised one; for verification);
  * r = NULL: quiet (0/1) */
 int simcuSetOption(simcu_ *r, char *name, double value);
