@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tpb", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0)
-    ap.add_argument("--maxregs", type=int, default=0)
+    ap.add_argument("--minblocks", type=int, default=0)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
@@ -222,8 +222,8 @@ def main():
         eng.set_option("threads_per_block", a.tpb)
     if a.lanes:
         eng.set_option("lanes_per_warp", a.lanes)
-    if a.maxregs:
-        eng.set_option("max_registers", a.maxregs)
+    if a.minblocks:
+        eng.set_option("min_blocks_per_sm", a.minblocks)
     eng.set_params(w.params)
     t0 = time.perf_counter()
     eng.prepare(w.tstep, w.tstop, 0.0, w.probes)

@@ -101,7 +101,7 @@ struct _simcu {
 	std::vector<int> probeRows;
 	int ngrid = 0, histRecords = 0, tpb = 64, wsShared = 1;
 	int interpreter = 0;            /* 1: run the batch on the generic kernels */
-	int maxRegs = 0;
+	int minBlocks = 0;              /* __launch_bounds__ second argument */
 	std::vector<char> active[2];
 	std::shared_ptr<JitKernel> jit;
 	std::vector<int> jitProbes;
@@ -496,7 +496,7 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "num_pilots") r->numPilots = std::max(1, (int)value);
 	else if (n == "interpreter") r->interpreter = (value != 0.0);
 	else if (n == "lanes_per_warp") r->lanesOpt = (int)value;
-	else if (n == "max_registers") { r->maxRegs = (int)value; r->jit.reset(); }
+	else if (n == "min_blocks_per_sm") { r->minBlocks = (int)value; r->jit.reset(); }
 	else return fail("unknown option %s", name);
 	r->prepared = false;
 	return 0;
@@ -694,15 +694,15 @@ std::map<std::string, std::shared_ptr<JitKernel> > gKernelCache;
 int buildJitKernel(simcu_ *r)
 {
 	if (r->jit && r->jitProbes == r->probeRows && r->jitTpb == r->tpb) return 0;
-	const std::string src = assembleSource(r->prog, r->sched, r->active, r->probeRows, r->tpb);
-	std::string key = src;
-	key += "//maxregs=" + std::to_string(r->maxRegs);
+	const std::string src = assembleSource(r->prog, r->sched, r->active, r->probeRows, r->tpb,
+			r->minBlocks);
+	const std::string &key = src;
 	std::map<std::string, std::shared_ptr<JitKernel> >::iterator it = gKernelCache.find(key);
 	if (it != gKernelCache.end()) r->jit = it->second;
 	else {
 		std::shared_ptr<JitKernel> k(new JitKernel());
 		std::string err;
-		if (!jitCompile(src, r->maxRegs, *k, err)) return fail("%s", err.c_str());
+		if (!jitCompile(src, *k, err)) return fail("%s", err.c_str());
 		if (!jitLoad(*k, r->tpb, err)) return fail("%s", err.c_str());
 		gKernelCache[key] = k;
 		r->jit = k;
@@ -827,13 +827,13 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		r->tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
 		r->wsShared = 0;
 		if (buildJitKernel(r)) return -1;
-		/* active lanes per warp: the fewest (power of two) that still keep
-		 * the whole batch resident at once */
+		/* active lanes per warp */
 		const int wpb = r->tpb / 32;
 		const long long capacity = (long long)sms * r->jit->maxBlocksPerSM * wpb;
 		int lanes = 32;
 		if (r->lanesOpt > 0) lanes = std::min(32, std::max(1, r->lanesOpt));
-		else while (lanes > 1 && ((long long)M + lanes / 2 - 1) / (lanes / 2) <= capacity) lanes /= 2;
+		/* (measured on B200: fewer than 32 lanes never paid off - the extra
+		 * warps thrash L1 with their local-memory windows - so 32 unless asked) */
 		int pow2 = 1;
 		while (pow2 * 2 <= lanes) pow2 *= 2;
 		r->lanes = pow2;
@@ -1173,11 +1173,11 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 			return fail("%s", err.c_str());
 	}
 	const int tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
-	const std::string src = assembleSource(p, sched, active, probeRows, tpb);
+	const std::string src = assembleSource(p, sched, active, probeRows, tpb, r->minBlocks);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;
 	std::string err;
-	if (!jitCompile(src, r->maxRegs, k, err)) return fail("%s", err.c_str());
+	if (!jitCompile(src, k, err)) return fail("%s", err.c_str());
 	if (cubinBytes) *cubinBytes = (int)k.cubin.size();
 	return 0;
 }

@@ -351,7 +351,7 @@ void emitRows(Out &o, const char *name, const std::vector<int> &rows)
 
 }  /* namespace */
 
-std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock)
+std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock, int minBlocks)
 {
 	Out o;
 	o.f("#define SIMCU_JIT 1\n");
@@ -359,7 +359,8 @@ std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock
 			p.N, p.nnzA, p.stateDoubles, p.stateInts);
 	o.f("#define SIMCU_NPARAM %d\n#define SIMCU_NISET %d\n#define SIMCU_NH %d\n",
 			(int)p.pmap.size(), p.niinst, (int)p.histRows.size());
-	o.f("#define SIMCU_NPROBES %d\n#define SIMCU_TPB %d\n", numProbes, threadsPerBlock);
+	o.f("#define SIMCU_NPROBES %d\n#define SIMCU_TPB %d\n#define SIMCU_MINB %d\n", numProbes,
+			threadsPerBlock, minBlocks > 0 ? minBlocks : 1);
 	o.f("#define HUGE_VAL (__longlong_as_double(0x7ff0000000000000LL))\n");
 	o.f("#define M_PI 3.14159265358979323846\n");
 	o.f("enum { SIMCU_OK = %d, SIMCU_ERR_TIMESTEP = %d, SIMCU_ERR_SINGULAR = %d, SIMCU_ERR_NAN = %d,\n"

@@ -13,14 +13,14 @@
 namespace simcu {
 
 /* #defines of the topology's sizes; first part of the translation unit */
-std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock);
+std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock, int minBlocks);
 /* device records, expressions and the unrolled LU of both phases */
 std::string generateTopology(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<int> &probeRows);
 /* prelude + embedded library headers + topology + kernel */
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<int> &probeRows,
-		int threadsPerBlock);
+		int threadsPerBlock, int minBlocks);
 
 /* A compiled kernel.  compile() needs no GPU (NVRTC only); load() does. */
 struct JitKernel {
@@ -33,8 +33,10 @@ struct JitKernel {
 	int maxBlocksPerSM = 0;
 	~JitKernel();
 };
-/* maxRegs = 0: let ptxas choose.  Returns false and fills err on failure. */
-bool jitCompile(const std::string &source, int maxRegs, JitKernel &k, std::string &err);
+/* Returns false and fills err on failure.  If the environment variable
+ * SIMCU_JIT_DUMP names a directory, the translation unit is also written there
+ * (and compiled under that path, so profilers can show the source). */
+bool jitCompile(const std::string &source, JitKernel &k, std::string &err);
 bool jitLoad(JitKernel &k, int threadsPerBlock, std::string &err);
 /* where libnvrtc was found ("" before the first compile) */
 const char *jitNvrtcPath();

@@ -35,8 +35,9 @@
  *     compile-time constants, so the compiler keeps the hot part in registers
  *     and spills the rest to local memory - which the hardware lays out exactly
  *     like the SoA above, one slot per RESIDENT thread instead of per instance.
- * S() is state addressed with constant slots; D() is the part of the state the
- * reference indexes with a ring counter (integrator and break-point rings).
+ * S() is state addressed with constant slots; D() (generic kernels only) is the
+ * part the reference indexes with a ring counter - the integrator and break-
+ * point rings, which the specialised kernel stores by age instead.
  * ------------------------------------------------------------------------ */
 #ifdef SIMCU_JIT
 #define SIMCU_UNROLL _Pragma("unroll")
@@ -54,21 +55,17 @@ struct Inst {
 	mutable double Av[SIMCU_DIM(SIMCU_NNZ)], Bv[SIMCU_DIM(SIMCU_N)];
 	mutable double Xv[SIMCU_DIM(SIMCU_N)], Xa[SIMCU_DIM(SIMCU_N)];
 	mutable double sv[SIMCU_DIM(SIMCU_SD)];
-	double *dv;          /* ring state: a separate local array, because one
-	                      * dynamically indexed member would pin the whole
-	                      * struct in memory */
 	mutable int iv[SIMCU_DIM(SIMCU_SI)];
 	double par[SIMCU_DIM(SIMCU_NPARAM)];
 	int tset[SIMCU_DIM(SIMCU_NISET)];
 
-	DEV Inst(const SimcuArgs &args, int inst, int slot, size_t stride, double *rings)
+	DEV Inst(const SimcuArgs &args, int inst, int slot, size_t stride)
 		: a(args), i(inst), hslot(slot), hstride(stride), hcount(0), npts(0), gridIdx(0),
-		  time(0.0), order(1), err(0), dv(rings) {}
+		  time(0.0), order(1), err(0) {}
 
 	DEV double P(int pid) const { return par[pid]; }
 	DEV int tableSet(int slot) const { return (slot >= 0) ? tset[slot] : 0; }
 	DEV double &S(int slot) const { return sv[slot]; }
-	DEV double &D(int slot) const { return dv[slot]; }
 	DEV int &IS(int slot) const { return iv[slot]; }
 	DEV void Aplus(int slot, double d) const { if (slot >= 0) Av[slot] += d; }
 	DEV void Aset(int slot, double v) const { if (slot >= 0) Av[slot] = v; }
@@ -190,6 +187,38 @@ DEV double pwGetNextX(const Table &t, int &index, double x0)
  * Break-point test: libs/simulator/math/checkbreak.c:43-67,71-95
  * state: x[3] t[3] theta[3] at sb, n at ib
  * ------------------------------------------------------------------------ */
+#ifdef SIMCU_JIT
+/* Specialised kernel: the rings are stored by AGE (0 = the slot of the current
+ * time point, 1 = the one before, ...) instead of by ring position n % 3, so
+ * every access has a compile-time index and the state can live in registers;
+ * advancing the ring counter becomes a rotation.  Same values, same tests. */
+DEV void cbInitialize(const Inst &c, int sb, int ib, double ic)
+{
+	SIMCU_UNROLL
+	for (int k = 0; k < 3; k++) { c.S(sb + k) = ic; c.S(sb + 3 + k) = 0.0; }
+	c.IS(ib) = 0;
+}
+
+DEV int cbIsBreak(const Inst &c, int sb, int ib, double x, double maxAngle)
+{
+	int n = c.IS(ib);
+	if (c.time > c.S(sb + 3)) {
+		n++; c.IS(ib) = n;
+		c.S(sb + 2) = c.S(sb + 1); c.S(sb + 1) = c.S(sb);               /* x */
+		c.S(sb + 5) = c.S(sb + 4); c.S(sb + 4) = c.S(sb + 3);           /* t */
+		c.S(sb + 8) = c.S(sb + 7); c.S(sb + 7) = c.S(sb + 6);           /* theta */
+	}
+	/* (n - 1) % 3 < 0 only while the counter is still 0: then p = slot 0 = k */
+	const bool prev = (n >= 1);
+	c.S(sb) = x;
+	c.S(sb + 3) = c.time;
+	const double xp = prev ? c.S(sb + 1) : x, tp = prev ? c.S(sb + 4) : c.time;
+	const double th = atan2(x - xp, c.time - tp);
+	c.S(sb + 6) = th;
+	const double thp = prev ? c.S(sb + 7) : th;
+	return (fabs(th - thp) > maxAngle) ? 1 : 0;
+}
+#else
 DEV void cbInitialize(const Inst &c, int sb, int ib, double ic)
 {
 	for (int k = 0; k < 3; k++) { c.D(sb + k) = ic; c.D(sb + 3 + k) = 0.0; }
@@ -210,6 +239,8 @@ DEV int cbIsBreak(const Inst &c, int sb, int ib, double x, double maxAngle)
 	c.D(sb + 6 + k) = th;
 	return (fabs(th - c.D(sb + 6 + p)) > maxAngle) ? 1 : 0;
 }
+
+#endif
 
 /* ------------------------------------------------------------------------ *
  * Newton convergence test: libs/simulator/math/checklinear.c:39-91
@@ -237,6 +268,105 @@ DEV int clIsLinear(const Inst &c, int sLast, int iState, double tol, double V,
  * the five rings t h x y f (4 each) contiguous, so the reference's negative
  * ring index at n == 1 (integrator.c:90-96) reads the same neighbours.
  * ------------------------------------------------------------------------ */
+DEV double DD1(double xnp1, double xn, double hn)
+{
+	return (hn == 0.0) ? 0.0 : ((xnp1 - xn) / hn);
+}
+DEV double DD2(double xnp1, double xn, double x1, double hn, double h1)
+{
+	return (DD1(xnp1, xn, hn) - DD1(xn, x1, h1)) / (hn + h1);
+}
+DEV double DD3(double xnp1, double xn, double x1, double x2, double hn, double h1, double h2)
+{
+	return (DD2(xnp1, xn, x1, hn, h1) - DD2(xn, x1, x2, h1, h2)) / (hn + h1 + h2);
+}
+
+#ifdef SIMCU_JIT
+/* Specialised kernel: rings by age.  AGE(k, a) is ring k (t h x y f) at the
+ * slot a steps behind the current one; a = 3 of the time ring is the "next"
+ * slot that holds the time of the present attempt.  The reference's negative
+ * ring index while the counter is below a (integrator.c:90-96, (n-a) % 4 < 0)
+ * lands on the same age of the previous ring; AGEQ reproduces that. */
+#define AGE(c, sb, k, a) (c).S((sb) + 2 + (k) * 4 + (a))
+#define AGEQ(c, sb, k, a, nn) (((nn) >= (a)) ? AGE(c, sb, k, a) : AGE(c, sb, (k) - 1, a))
+enum { RT = 0, RH = 1, RX = 2, RY = 3, RF = 4 };
+
+DEV void itInitialize(const Inst &c, int sb, int ib, double ic, double ydtdx)
+{
+	c.S(sb) = 0.0; c.S(sb + 1) = 0.0; c.IS(ib) = 0;
+	SIMCU_UNROLL
+	for (int j = 0; j < 4; j++) {
+		AGE(c, sb, RT, j) = 0.0; AGE(c, sb, RH, j) = c.a.ctl.tstop;
+		AGE(c, sb, RY, j) = 0.0; AGE(c, sb, RX, j) = ic; AGE(c, sb, RF, j) = ydtdx;
+	}
+}
+
+/* integrator.c:106-163 */
+DEV void itIntegrate(Inst &c, int sb, int ib, double x0, double ydtdx,
+		double &dydx0, double &y0)
+{
+	if (isnan(x0)) { c.err = SIMCU_ERR_NAN; return; }
+	const double t0 = c.time;
+	int nn = c.IS(ib);
+	if (t0 > AGE(c, sb, RT, 3)) {
+		nn++; c.IS(ib) = nn;
+		const double tNext = AGE(c, sb, RT, 3);
+		AGE(c, sb, RT, 3) = AGE(c, sb, RT, 2); AGE(c, sb, RT, 2) = AGE(c, sb, RT, 1);
+		AGE(c, sb, RT, 1) = AGE(c, sb, RT, 0); AGE(c, sb, RT, 0) = tNext;
+		SIMCU_UNROLL
+		for (int k = RH; k <= RF; k++) {
+			AGE(c, sb, k, 2) = AGE(c, sb, k, 1); AGE(c, sb, k, 1) = AGE(c, sb, k, 0);
+		}
+	}
+	const double h = t0 - AGE(c, sb, RT, 0);
+	AGE(c, sb, RH, 0) = h;
+	AGE(c, sb, RT, 3) = t0;
+	AGE(c, sb, RX, 0) = x0;
+	const double yn = c.S(sb + 1) * x0 - c.S(sb);
+	AGE(c, sb, RY, 0) = yn;
+	AGE(c, sb, RF, 0) = ydtdx;
+	const double fp = AGEQ(c, sb, RF, 1, nn);
+	if (c.order < 2) {
+		dydx0 = fp / h;
+		y0 = dydx0 * x0;
+	} else {
+		dydx0 = 2.0 * ydtdx / h;
+		double mult = ydtdx / fp;
+		if (isnan(mult)) mult = 1 / c.a.ctl.gmin;
+		y0 = dydx0 * x0 + mult * yn;
+	}
+	c.S(sb + 1) = dydx0;
+	c.S(sb) = y0;
+}
+
+/* integrator.c:61-102 (LTE step recommendation; float sqrtf at :99) */
+DEV double itNextStep(Inst &c, int sb, int ib, double x0, double ydtdx, double abstol)
+{
+	if (isnan(x0)) { c.err = SIMCU_ERR_NAN; return 0.0; }
+	const SimcuControl &k = c.a.ctl;
+	const int nn = c.IS(ib);
+	const double y0 = c.S(sb + 1) * x0 - c.S(sb);
+	const double ey = k.reltol * MaxAbs(AGE(c, sb, RY, 0), y0) + abstol;
+	const double hn = AGE(c, sb, RH, 0), xn = AGE(c, sb, RX, 0);
+	const double eyp = k.reltol * MaxAbs(MaxAbs(x0, xn) * (ydtdx / hn), k.chgtol);
+	const double e = MaxAbs(eyp, ey);
+	const double f1 = AGEQ(c, sb, RF, 1, nn), x1 = AGEQ(c, sb, RX, 1, nn), h1 = AGEQ(c, sb, RH, 1, nn);
+	double h, dd;
+	if (c.order < 2) {
+		dd = DD2((ydtdx * x0), (AGE(c, sb, RF, 0) * xn), (f1 * x1), hn, h1);
+		dd *= 1.0 / 2.0;
+		h = k.trtol * e / MaxAbs(dd, abstol);
+	} else {
+		const double f2 = AGEQ(c, sb, RF, 2, nn), x2 = AGEQ(c, sb, RX, 2, nn);
+		const double h2 = AGEQ(c, sb, RH, 2, nn);
+		dd = DD3((ydtdx * x0), (AGE(c, sb, RF, 0) * xn), (f1 * x1), (f2 * x2), hn, h1, h2);
+		dd *= 1.0 / 12.0;
+		h = sqrtf(k.trtol * e / MaxAbs(dd, abstol));
+	}
+	if (isnan(h)) c.err = SIMCU_ERR_NAN;
+	return h;
+}
+#else
 #define RING(c, sb, k, j) (c).D((sb) + 2 + (k) * 4 + (j))
 enum { RT = 0, RH = 1, RX = 2, RY = 3, RF = 4 };
 
@@ -278,19 +408,6 @@ DEV void itIntegrate(Inst &c, int sb, int ib, double x0, double ydtdx,
 	c.D(sb) = y0;
 }
 
-DEV double DD1(double xnp1, double xn, double hn)
-{
-	return (hn == 0.0) ? 0.0 : ((xnp1 - xn) / hn);
-}
-DEV double DD2(double xnp1, double xn, double x1, double hn, double h1)
-{
-	return (DD1(xnp1, xn, hn) - DD1(xn, x1, h1)) / (hn + h1);
-}
-DEV double DD3(double xnp1, double xn, double x1, double x2, double hn, double h1, double h2)
-{
-	return (DD2(xnp1, xn, x1, hn, h1) - DD2(xn, x1, x2, h1, h2)) / (hn + h1 + h2);
-}
-
 /* integrator.c:61-102 (LTE step recommendation; float sqrtf at :99) */
 DEV double itNextStep(Inst &c, int sb, int ib, double x0, double ydtdx, double abstol)
 {
@@ -320,6 +437,8 @@ DEV double itNextStep(Inst &c, int sb, int ib, double x0, double ydtdx, double a
 	if (isnan(h)) c.err = SIMCU_ERR_NAN;
 	return h;
 }
+
+#endif
 
 /* ------------------------------------------------------------------------ *
  * Source waveforms: libs/simulator/math/waveform.c:169-338 with the default

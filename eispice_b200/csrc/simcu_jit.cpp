@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -77,9 +78,9 @@ void jitSetNvrtcPath(const char *path) { gNvrtcHint = path ? path : ""; }
 
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<int> &probeRows,
-		int threadsPerBlock)
+		int threadsPerBlock, int minBlocks)
 {
-	std::string s = generatePrelude(p, (int)probeRows.size(), threadsPerBlock);
+	std::string s = generatePrelude(p, (int)probeRows.size(), threadsPerBlock, minBlocks);
 	s += kSrcProgram;
 	s += kSrcCalc;
 	s += kSrcDevice;
@@ -93,18 +94,21 @@ JitKernel::~JitKernel()
 	if (library) cudaLibraryUnload((cudaLibrary_t)library);
 }
 
-bool jitCompile(const std::string &source, int maxRegs, JitKernel &k, std::string &err)
+bool jitCompile(const std::string &source, JitKernel &k, std::string &err)
 {
 	if (!openNvrtc(err)) return false;
+	std::string name = "simcu_topology.cu";
+	if (const char *dir = std::getenv("SIMCU_JIT_DUMP")) {
+		char file[64];
+		std::snprintf(file, sizeof file, "/simcu_topology_%016zx.cu", std::hash<std::string>()(source));
+		name = std::string(dir) + file;
+		if (FILE *f = std::fopen(name.c_str(), "w")) { std::fwrite(source.data(), 1, source.size(), f); std::fclose(f); }
+	}
 	nvrtcProgram prog = nullptr;
-	nvrtcResult rc = gNvrtc.createProgram(&prog, source.c_str(), "simcu_topology.cu", 0, nullptr, nullptr);
+	nvrtcResult rc = gNvrtc.createProgram(&prog, source.c_str(), name.c_str(), 0, nullptr, nullptr);
 	if (rc != NVRTC_SUCCESS) { err = gNvrtc.errorString(rc); return false; }
-	char regs[64];
-	std::snprintf(regs, sizeof regs, "--maxrregcount=%d", maxRegs);
 	std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
-		"--fmad=true", "-default-device"};
-	opts.pop_back();
-	if (maxRegs > 0) opts.push_back(regs);
+		"--fmad=true"};
 	rc = gNvrtc.compileProgram(prog, (int)opts.size(), opts.data());
 	size_t logSize = 0;
 	gNvrtc.getLogSize(prog, &logSize);

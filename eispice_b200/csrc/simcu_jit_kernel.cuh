@@ -17,8 +17,7 @@
 
 DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, int opOnly)
 {
-	double rings[SIMCU_DIM(SIMCU_SD)];
-	Inst c(a, inst, slot, hstride, rings);
+	Inst c(a, inst, slot, hstride);
 	const SimcuControl &k = a.ctl;
 	const size_t M = a.M;
 
@@ -41,7 +40,7 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 	SIMCU_UNROLL
 	for (int r = 0; r < SIMCU_N; r++) { c.Bv[r] = 0.0; c.Xv[r] = 0.0; c.Xa[r] = 0.0; }
 	SIMCU_UNROLL
-	for (int s = 0; s < SIMCU_SD; s++) { c.sv[s] = 0.0; rings[s] = 0.0; }
+	for (int s = 0; s < SIMCU_SD; s++) c.sv[s] = 0.0;
 	SIMCU_UNROLL
 	for (int s = 0; s < SIMCU_SI; s++) c.iv[s] = 0;
 
@@ -145,7 +144,7 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 	ci[(size_t)CI_NPTS * M] = c.npts;
 }
 
-extern "C" __global__ void __launch_bounds__(SIMCU_TPB) simcuJitKernel(const SimcuArgs a, int opOnly)
+extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKernel(const SimcuArgs a, int opOnly)
 {
 	/* a.lanes < 32 spreads a batch that is too small to fill the machine over
 	 * more warps (fewer instances per warp): the kernel is latency-bound, so

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One batched transient of a workload, for ncu: prepare, one warm-up run, one
-profiled run.  Usage: profile_run.py <cfg> <instances> [tpb]"""
+profiled run.  Usage: profile_run.py <cfg> <instances> [min_blocks_per_sm]"""
 import os
 import sys
 
@@ -13,7 +13,7 @@ name, M = sys.argv[1], int(sys.argv[2])
 w = workloads.make(name, M)
 eng = engine.Engine(w.cct.netlist(), w.M)
 if len(sys.argv) > 3:
-    eng.set_option("threads_per_block", int(sys.argv[3]))
+    eng.set_option("min_blocks_per_sm", int(sys.argv[3]))
 eng.set_params(w.params)
 eng.prepare(w.tstep, w.tstop, 0.0, w.probes)
 eng.upload()
