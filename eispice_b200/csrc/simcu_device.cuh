@@ -11,6 +11,13 @@
 #define SIMCU_DEVICE_CUH
 
 #define DEV __device__ __forceinline__
+/* Heavy, state-free helpers are real functions: the specialised kernel inlines
+ * one copy of every device per netlist entry, and without this its code
+ * outgrows the instruction cache (measured: stall_no_inst was the top stall). */
+#define DEVFN __device__ __noinline__
+
+DEVFN double simcuAtan2(double y, double x) { return atan2(y, x); }
+DEVFN double simcuExp(double x) { return exp(x); }
 
 #define MaxAbs(x, y) ((fabs(x) > fabs(y)) ? fabs(x) : fabs(y))
 #define Min3(x, y, z) ((x < y) ? ((z < x) ? z : x) : ((z < y) ? z : y))
@@ -150,18 +157,25 @@ DEV int pwSetIndex(const Table &t, int index, double x0)
 	return index;
 }
 
-DEV void pwCalcValue(const Table &t, int &index, double x0, double &y0, double &dydx0)
+struct PwValue { double y, dydx; int index; };
+
+DEVFN PwValue pwCalcValueFn(const double *tx, const double *ty, const double *tm, int len,
+		int type, int index, double x0)
 {
+	Table t;
+	t.x = tx; t.y = ty; t.m = tm; t.len = len; t.type = type;
+	PwValue r;
 	index = pwSetIndex(t, index, x0);
+	r.index = index;
 	const int i = index;
 	if ((i == 0) || (i >= t.len - 2)) {
-		if (__ldg(&t.x[0]) > x0) { y0 = __ldg(&t.y[0]); dydx0 = 0; return; }
-		if (__ldg(&t.x[t.len - 1]) < x0) { y0 = __ldg(&t.y[t.len - 1]); dydx0 = 0; return; }
+		if (__ldg(&t.x[0]) > x0) { r.y = __ldg(&t.y[0]); r.dydx = 0; return r; }
+		if (__ldg(&t.x[t.len - 1]) < x0) { r.y = __ldg(&t.y[t.len - 1]); r.dydx = 0; return r; }
 	}
 	if (t.type == 'l') {
 		const double mi = __ldg(&t.m[i]);
-		y0 = __ldg(&t.y[i]) + mi * (x0 - __ldg(&t.x[i]));
-		dydx0 = mi;
+		r.y = __ldg(&t.y[i]) + mi * (x0 - __ldg(&t.x[i]));
+		r.dydx = mi;
 	} else {
 		const double xi = __ldg(&t.x[i]), yi = __ldg(&t.y[i]);
 		const double mi = __ldg(&t.m[i]), mi1 = __ldg(&t.m[i + 1]);
@@ -170,9 +184,16 @@ DEV void pwCalcValue(const Table &t, int &index, double x0, double &y0, double &
 		const double pa = dy / dx - dx * (mi1 + mi * 2.0) / 6.0;
 		const double pb = 0.5 * mi;
 		const double pc = (mi1 - mi) / (6.0 * dx);
-		y0 = yi + dx0 * (pa + dx0 * (pb + dx0 * pc));
-		dydx0 = pa + dx0 * (2 * pb + 3 * pc * dx0);
+		r.y = yi + dx0 * (pa + dx0 * (pb + dx0 * pc));
+		r.dydx = pa + dx0 * (2 * pb + 3 * pc * dx0);
 	}
+	return r;
+}
+
+DEV void pwCalcValue(const Table &t, int &index, double x0, double &y0, double &dydx0)
+{
+	const PwValue r = pwCalcValueFn(t.x, t.y, t.m, t.len, t.type, index, x0);
+	index = r.index; y0 = r.y; dydx0 = r.dydx;
 }
 
 /* piecewise.c:204-222 with its two dead branches */
@@ -213,7 +234,7 @@ DEV int cbIsBreak(const Inst &c, int sb, int ib, double x, double maxAngle)
 	c.S(sb) = x;
 	c.S(sb + 3) = c.time;
 	const double xp = prev ? c.S(sb + 1) : x, tp = prev ? c.S(sb + 4) : c.time;
-	const double th = atan2(x - xp, c.time - tp);
+	const double th = simcuAtan2(x - xp, c.time - tp);
 	c.S(sb + 6) = th;
 	const double thp = prev ? c.S(sb + 7) : th;
 	return (fabs(th - thp) > maxAngle) ? 1 : 0;
@@ -235,7 +256,7 @@ DEV int cbIsBreak(const Inst &c, int sb, int ib, double x, double maxAngle)
 	if (p < 0) p = 0;
 	c.D(sb + k) = x;
 	c.D(sb + 3 + k) = c.time;
-	const double th = atan2(x - c.D(sb + p), c.time - c.D(sb + 3 + p));
+	const double th = simcuAtan2(x - c.D(sb + p), c.time - c.D(sb + 3 + p));
 	c.D(sb + 6 + k) = th;
 	return (fabs(th - c.D(sb + 6 + p)) > maxAngle) ? 1 : 0;
 }
@@ -340,29 +361,36 @@ DEV void itIntegrate(Inst &c, int sb, int ib, double x0, double ydtdx,
 }
 
 /* integrator.c:61-102 (LTE step recommendation; float sqrtf at :99) */
+DEVFN double itNextStepFn(int order, double reltol, double chgtol, double trtol, double abstol,
+		double x0, double ydtdx, double ieq, double g, double ry0, double hn, double xn, double fn,
+		double f1, double x1, double h1, double f2, double x2, double h2)
+{
+	const double y0 = g * x0 - ieq;
+	const double ey = reltol * MaxAbs(ry0, y0) + abstol;
+	const double eyp = reltol * MaxAbs(MaxAbs(x0, xn) * (ydtdx / hn), chgtol);
+	const double e = MaxAbs(eyp, ey);
+	double h, dd;
+	if (order < 2) {
+		dd = DD2((ydtdx * x0), (fn * xn), (f1 * x1), hn, h1);
+		dd *= 1.0 / 2.0;
+		h = trtol * e / MaxAbs(dd, abstol);
+	} else {
+		dd = DD3((ydtdx * x0), (fn * xn), (f1 * x1), (f2 * x2), hn, h1, h2);
+		dd *= 1.0 / 12.0;
+		h = sqrtf(trtol * e / MaxAbs(dd, abstol));
+	}
+	return h;
+}
+
 DEV double itNextStep(Inst &c, int sb, int ib, double x0, double ydtdx, double abstol)
 {
 	if (isnan(x0)) { c.err = SIMCU_ERR_NAN; return 0.0; }
 	const SimcuControl &k = c.a.ctl;
 	const int nn = c.IS(ib);
-	const double y0 = c.S(sb + 1) * x0 - c.S(sb);
-	const double ey = k.reltol * MaxAbs(AGE(c, sb, RY, 0), y0) + abstol;
-	const double hn = AGE(c, sb, RH, 0), xn = AGE(c, sb, RX, 0);
-	const double eyp = k.reltol * MaxAbs(MaxAbs(x0, xn) * (ydtdx / hn), k.chgtol);
-	const double e = MaxAbs(eyp, ey);
-	const double f1 = AGEQ(c, sb, RF, 1, nn), x1 = AGEQ(c, sb, RX, 1, nn), h1 = AGEQ(c, sb, RH, 1, nn);
-	double h, dd;
-	if (c.order < 2) {
-		dd = DD2((ydtdx * x0), (AGE(c, sb, RF, 0) * xn), (f1 * x1), hn, h1);
-		dd *= 1.0 / 2.0;
-		h = k.trtol * e / MaxAbs(dd, abstol);
-	} else {
-		const double f2 = AGEQ(c, sb, RF, 2, nn), x2 = AGEQ(c, sb, RX, 2, nn);
-		const double h2 = AGEQ(c, sb, RH, 2, nn);
-		dd = DD3((ydtdx * x0), (AGE(c, sb, RF, 0) * xn), (f1 * x1), (f2 * x2), hn, h1, h2);
-		dd *= 1.0 / 12.0;
-		h = sqrtf(k.trtol * e / MaxAbs(dd, abstol));
-	}
+	const double h = itNextStepFn(c.order, k.reltol, k.chgtol, k.trtol, abstol, x0, ydtdx,
+			c.S(sb), c.S(sb + 1), AGE(c, sb, RY, 0), AGE(c, sb, RH, 0), AGE(c, sb, RX, 0),
+			AGE(c, sb, RF, 0), AGEQ(c, sb, RF, 1, nn), AGEQ(c, sb, RX, 1, nn), AGEQ(c, sb, RH, 1, nn),
+			AGEQ(c, sb, RF, 2, nn), AGEQ(c, sb, RX, 2, nn), AGEQ(c, sb, RH, 2, nn));
 	if (isnan(h)) c.err = SIMCU_ERR_NAN;
 	return h;
 }
@@ -820,34 +848,38 @@ DEV void devInitStep(Inst &c, const int *d)
 /* T-line delayed lookup: history_interp.c:42-92, history.c:36-59.  Records
  * are kept in a ring of a.histRecords entries; `count` records exist so far,
  * record r lives in slot r % R.  Returns false if the needed record is gone. */
-DEV bool histLocate(Inst &c, int ib, double tp, int &iP, int &iN)
-{
-	const SimcuArgs &a = c.a;
-	const int count = c.hcount, R = a.histRecords;
-	const int lo = (count > R) ? count - R : 0;
-	int i = c.IS(ib + 2);
-	if (i < lo || i >= count) i = lo;
-	#define HT(r) a.Ht[(size_t)((r) % R) * c.hstride + c.hslot]
-	while (HT(i) > tp && i > lo) i--;
-	if (HT(i) > tp) return false;             /* fell off the ring */
-	while (i + 1 < count && HT(i + 1) <= tp) i++;
-	#undef HT
-	c.IS(ib + 2) = i;
-	if (i + 1 < count) { iP = i; iN = i + 1; }
-	else { if (i - 1 < lo) return false; iP = i - 1; iN = i; }
-	return true;
-}
+struct TlinePast { double v[6]; int hint; int ok; };
 
-DEV double histInterp(const Inst &c, int iP, int iN, int col, double tp)
+DEVFN TlinePast tlinePastFn(const double *Ht, const double *Hx, int R, int nh, size_t hstride,
+		int hslot, int count, int hint, double tp, int c0, int c1, int c2, int c3, int c4, int c5)
 {
-	if (col < 0) return 0.0;
-	const SimcuArgs &a = c.a;
-	const int R = a.histRecords;
-	const double tP = a.Ht[(size_t)(iP % R) * c.hstride + c.hslot];
-	const double tN = a.Ht[(size_t)(iN % R) * c.hstride + c.hslot];
-	const double xP = a.Hx[((size_t)(iP % R) * a.nh + col) * c.hstride + c.hslot];
-	const double xN = a.Hx[((size_t)(iN % R) * a.nh + col) * c.hstride + c.hslot];
-	return ((xN - xP) / (tN - tP)) * (tp - tP) + xP;
+	TlinePast r;
+	r.ok = 0; r.hint = hint;
+	#pragma unroll
+	for (int j = 0; j < 6; j++) r.v[j] = 0.0;
+	const int lo = (count > R) ? count - R : 0;
+	int i = hint;
+	if (i < lo || i >= count) i = lo;
+	#define HT(q) Ht[(size_t)((q) % R) * hstride + hslot]
+	while (HT(i) > tp && i > lo) i--;
+	if (HT(i) > tp) return r;                 /* fell off the ring */
+	while (i + 1 < count && HT(i + 1) <= tp) i++;
+	r.hint = i;
+	int iP, iN;
+	if (i + 1 < count) { iP = i; iN = i + 1; }
+	else { if (i - 1 < lo) return r; iP = i - 1; iN = i; }
+	const double tP = HT(iP), tN = HT(iN);
+	#undef HT
+	const int cols[6] = {c0, c1, c2, c3, c4, c5};
+	#pragma unroll
+	for (int j = 0; j < 6; j++) {
+		if (cols[j] < 0) continue;
+		const double xP = Hx[((size_t)(iP % R) * nh + cols[j]) * hstride + hslot];
+		const double xN = Hx[((size_t)(iN % R) * nh + cols[j]) * hstride + hslot];
+		r.v[j] = ((xN - xP) / (tN - tP)) * (tp - tP) + xP;
+	}
+	r.ok = 1;
+	return r;
 }
 
 DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
@@ -882,12 +914,12 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 			Ir = 0.0; Is = 0.0;
 			Vk = c.S(sb + 2); Vj = c.S(sb + 3); Vl = c.S(sb + 4); Vm = c.S(sb + 5);
 		} else {
-			int iP, iN;
-			if (!histLocate(c, ib, tp, iP, iN)) { c.err = SIMCU_ERR_HISTORY; return 0; }
 			const int *h = d + DF_TH0;              /* R S K J L M */
-			Ir = histInterp(c, iP, iN, h[0], tp); Is = histInterp(c, iP, iN, h[1], tp);
-			Vk = histInterp(c, iP, iN, h[2], tp); Vj = histInterp(c, iP, iN, h[3], tp);
-			Vl = histInterp(c, iP, iN, h[4], tp); Vm = histInterp(c, iP, iN, h[5], tp);
+			const TlinePast r = tlinePastFn(c.a.Ht, c.a.Hx, c.a.histRecords, c.a.nh, c.hstride,
+					c.hslot, c.hcount, c.IS(ib + 2), tp, h[0], h[1], h[2], h[3], h[4], h[5]);
+			if (!r.ok) { c.err = SIMCU_ERR_HISTORY; return 0; }
+			c.IS(ib + 2) = r.hint;
+			Ir = r.v[0]; Is = r.v[1]; Vk = r.v[2]; Vj = r.v[3]; Vl = r.v[4]; Vm = r.v[5];
 		}
 		const double z0 = c.P(d[DF_PZ0]), loss = c.P(d[DF_PLOSS]);
 		double Vr, Vs;
@@ -895,8 +927,8 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 			Vr = (Vl - Vm) + z0 * Is;
 			Vs = (Vk - Vj) + z0 * Ir;
 		} else {
-			Vr = exp(-loss / 2) * ((Vl - Vm) + z0 * Is);
-			Vs = exp(-loss / 2) * ((Vk - Vj) + z0 * Ir);
+			Vr = simcuExp(-loss / 2) * ((Vl - Vm) + z0 * Is);
+			Vs = simcuExp(-loss / 2) * ((Vk - Vj) + z0 * Ir);
 		}
 		c.Bplus(d[DF_ROWR], Vr - c.S(sb)); c.S(sb) = Vr;
 		c.Bplus(d[DF_ROWS], Vs - c.S(sb + 1)); c.S(sb + 1) = Vs;
