@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--tpb", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--minblocks", type=int, default=0)
+    ap.add_argument("--maxblocks", type=int, default=0)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
@@ -224,6 +225,8 @@ def main():
         eng.set_option("lanes_per_warp", a.lanes)
     if a.minblocks:
         eng.set_option("min_blocks_per_sm", a.minblocks)
+    if a.maxblocks:
+        eng.set_option("max_blocks_per_sm", a.maxblocks)
     eng.set_params(w.params)
     t0 = time.perf_counter()
     eng.prepare(w.tstep, w.tstop, 0.0, w.probes)
@@ -283,6 +286,8 @@ def main():
         launches += eng.stats()["kernelLaunches"] + 1
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    codes, counts = np.unique(status, return_counts=True)
+    status_hist = {engine.STATUS.get(int(c), str(int(c))): int(n) for c, n in zip(codes, counts)}
     clocks = sampler.stop() if rank == 0 else None
     barrier()
 
@@ -324,7 +329,7 @@ def main():
                        "registers_per_thread": st["registersPerThread"],
                        "local_bytes_per_thread": st["localBytesPerThread"],
                        "l2": "flushed between timed steps (256 MiB write)",
-                       "failed_instances": int(failed_all),
+                       "failed_instances": int(failed_all), "status_rank0": status_hist,
                        "prepare_s": round(prepare_s, 3)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},

@@ -102,6 +102,7 @@ struct _simcu {
 	int ngrid = 0, histRecords = 0, tpb = 64, wsShared = 1;
 	int interpreter = 0;            /* 1: run the batch on the generic kernels */
 	int minBlocks = 0;              /* __launch_bounds__ second argument */
+	int maxBlocksPerSM = 0;         /* cap on resident blocks (0 = occupancy limit) */
 	std::vector<char> active[2];
 	std::shared_ptr<JitKernel> jit;
 	std::vector<int> jitProbes;
@@ -497,6 +498,7 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "interpreter") r->interpreter = (value != 0.0);
 	else if (n == "lanes_per_warp") r->lanesOpt = (int)value;
 	else if (n == "min_blocks_per_sm") { r->minBlocks = (int)value; r->jit.reset(); }
+	else if (n == "max_blocks_per_sm") r->maxBlocksPerSM = (int)value;
 	else return fail("unknown option %s", name);
 	r->prepared = false;
 	return 0;
@@ -829,7 +831,9 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		if (buildJitKernel(r)) return -1;
 		/* active lanes per warp */
 		const int wpb = r->tpb / 32;
-		const long long capacity = (long long)sms * r->jit->maxBlocksPerSM * wpb;
+		int perSM = r->jit->maxBlocksPerSM;
+		if (r->maxBlocksPerSM > 0) perSM = std::min(perSM, r->maxBlocksPerSM);
+		const long long capacity = (long long)sms * perSM * wpb;
 		int lanes = 32;
 		if (r->lanesOpt > 0) lanes = std::min(32, std::max(1, r->lanesOpt));
 		/* (measured on B200: fewer than 32 lanes never paid off - the extra
@@ -1064,6 +1068,21 @@ int simcuGetStats(simcu_ *r, simcuStats_ *stats)
 	if (r->ran && collectStats(r)) return -1;
 	*stats = r->stats;
 	return 0;
+}
+
+int simcuFetchCounters(simcu_ *r, char *which, int *out)
+{
+	if (!r || !r->ran || !which || !out) return -1;
+	static const struct { const char *name; int row; } rows[] = {
+		{"status", CI_STATUS}, {"accepted", CI_ACCEPTED}, {"rejected_lte", CI_REJ_LTE},
+		{"rejected_nc", CI_REJ_NC}, {"factorizations", CI_NFACT}, {"op_factorizations", CI_NFACT_OP}};
+	for (size_t i = 0; i < sizeof rows / sizeof rows[0]; i++)
+		if (!std::strcmp(which, rows[i].name)) {
+			CU(cudaMemcpy(out, r->dCI.as<int>() + (size_t)rows[i].row * r->M, (size_t)r->M * 4,
+					cudaMemcpyDeviceToHost));
+			return 0;
+		}
+	return fail("unknown counter %s", which);
 }
 
 int simcuFetchRaw(simcu_ *r, int instance, double *data[], int *numPoints, int *numVariables)

@@ -139,6 +139,11 @@ bool jitLoad(JitKernel &k, int threadsPerBlock, std::string &err)
 	e = cudaLibraryGetKernel(&kern, lib, "simcuJitKernel");
 	if (e != cudaSuccess) { err = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e); return false; }
 	k.kernel = kern;
+	/* no shared memory is used: give the whole SM array to L1, where the
+	 * spilled part of the thread-local state lives */
+	if (cudaFuncSetAttribute((const void *)kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0)
+			!= cudaSuccess)
+		cudaGetLastError();
 	cudaFuncAttributes attr;
 	if (cudaFuncGetAttributes(&attr, (const void *)kern) == cudaSuccess) {
 		k.numRegs = attr.numRegs;

@@ -94,6 +94,7 @@ def lib():
     L.simcuDeviceOutput.argtypes = [vp]
     L.simcuGetStats.argtypes = [vp, vp]
     L.simcuFetchRaw.argtypes = [vp, C.c_int, vp, ip, ip]
+    L.simcuFetchCounters.argtypes = [vp, cp, vp]
     L.simcuNumUnknowns.argtypes = [vp]
     L.simcuNumNonzeros.argtypes = [vp]
     L.simcuGetPattern.argtypes = [vp, vp, vp]
@@ -364,6 +365,13 @@ class Engine:
 
     def device_output_ptr(self):
         return self.L.simcuDeviceOutput(self.h)
+
+    def counters(self, which):
+        """Per-instance counter array of the last batch ('accepted', 'factorizations', ...)."""
+        out = np.empty(self.num_instances, dtype=np.int32)
+        if self.L.simcuFetchCounters(self.h, _b(which), out.ctypes.data):
+            raise KeyError(which)
+        return out
 
     def fetch_raw(self, instance):
         data = C.POINTER(C.c_double)()

@@ -180,6 +180,10 @@ int simcuNumGrid(simcu_ *r);
 /* device pointer of the gridded output, layout [numGrid][numProbes][M] */
 void *simcuDeviceOutput(simcu_ *r);
 int simcuGetStats(simcu_ *r, simcuStats_ *stats);
+/* per-instance counters of the last batch into out[numInstances]; which is
+ * status, accepted, rejected_lte, rejected_nc, factorizations or
+ * op_factorizations */
+int simcuFetchCounters(simcu_ *r, char *which, int *out);
 /* raw (time, X) record of one instance of the last batch, reference layout
  * (core/matrix.c:430-470): malloc'd [numPoints][numVariables], column 0 = time.
  * Needs the options raw_max_points > 0 and raw_first / raw_count covering it. */
