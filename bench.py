@@ -170,6 +170,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def other_workloads(a, peak):
+    """Informational: the north-star IBIS configurations at a single-GPU size,
+    one warm-up + one timed batch each (device-resident timing only)."""
+    import workloads
+    from eispice_b200 import engine
+    out = []
+    for name, M in (("cfg4", 65536), ("cfg5", 32768)):
+        try:
+            w = workloads.make(name, M)
+            eng = engine.Engine(w.cct.netlist(), w.M)
+            eng.set_params(w.params)
+            eng.prepare(w.tstep, w.tstop, 0.0, w.probes)
+            eng.upload()
+            eng.run_device()
+            eng.run_device()
+            st = eng.stats()
+            n_tlines = sum(1 for d in w.cct.netlist() if d[0] == "T")
+            balg, k = workloads.algorithmic_bytes(st, n_tlines, len(w.probes))
+            rate = st["accepted"] / (st["deviceMs"] * 1e-3)
+            out.append({"workload": "%s: %s" % (name, workloads.DESCRIPTION[name]),
+                        "instances": M, "value": rate, "unit": UNIT,
+                        "ms_per_step": st["deviceMs"], "solves_per_timestep": round(k, 3),
+                        "bytes_per_instance_timestep": round(balg, 1),
+                        "roofline_frac": balg * rate / 1e9 / peak,
+                        "failed_instances": st["failed"],
+                        "registers_per_thread": st["registersPerThread"]})
+            eng.close()
+        except Exception as e:  # noqa: BLE001
+            out.append({"workload": name, "error": str(e)})
+    return out
+
+
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
@@ -183,6 +215,8 @@ def main():
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", action="store_true",
+                    help="also time cfg4/cfg5 once (adds ~1 min)")
     ap.add_argument("--tpb", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--minblocks", type=int, default=0)
@@ -341,6 +375,18 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             "clocks": clocks,
         }
+        # measured DRAM traffic of the dominant kernel, per launch, from the committed
+        # ncu capture of this same workload (profiles/summary.json), else null
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "summary.json")))
+            ent = prof.get("%s@%d" % (name, w.M))
+            if ent:
+                line["roofline"]["traffic"] = ent["dram_bytes_per_launch"]
+                line["roofline"]["traffic_source"] = ent["source"]
+        except (OSError, ValueError, KeyError):
+            pass
+        if world == 1 and a.extras:
+            line["other_workloads"] = other_workloads(a, peak)
         if world == 1 and not a.no_cpu_baseline:
             try:
                 rate, cores, kind, sample = cpu_reference_rate(name, w.M, a.cpu_seconds)

@@ -111,7 +111,7 @@ struct _simcu {
 	simcuStats_ stats;
 	/* device memory */
 	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
-		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabX, dTabY, dTabM, dHistRows,
+		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
 		dProbeRows, dPmap, dPconst, dPinst, dIinst;
 	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dOutRaw, dWs, dRemaining;
 	int *hRemaining = nullptr;      /* pinned */
@@ -131,8 +131,8 @@ struct _simcu {
 	~_simcu()
 	{
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
-			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabX,
-			&dTabY, &dTabM, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
+			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP,
+			&dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
 			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dOutRaw,
 			&dWs, &dRemaining};
 		for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) all[i]->release();
@@ -543,16 +543,14 @@ int uploadParameters(simcu_ *r, cudaStream_t st)
 	if (r->dPmap.upload(p.pmap, st) || r->dPconst.upload(p.pconst, st) ||
 			r->dPinst.upload(p.pinst, st) || r->dIinst.upload(p.iinst, st) ||
 			r->dTabOff.upload(p.tabOff, st) || r->dTabType.upload(p.tabType, st) ||
-			r->dTabX.upload(p.tabX, st) || r->dTabY.upload(p.tabY, st) ||
-			r->dTabM.upload(p.tabM, st))
+			r->dTabP.upload(p.tabP, st))
 		return -1;
 	for (int ph = 0; ph < 2; ph++) {
 		SimcuArgs &a = r->args[ph];
 		a.pmap = r->dPmap.as<int>(); a.pconst = r->dPconst.as<double>();
 		a.pinst = r->dPinst.as<double>(); a.iinst = r->dIinst.as<int>();
 		a.tabOff = r->dTabOff.as<int>(); a.tabType = r->dTabType.as<int>();
-		a.tabX = r->dTabX.as<double>(); a.tabY = r->dTabY.as<double>();
-		a.tabM = r->dTabM.as<double>();
+		a.tabP = r->dTabP.as<double>();
 	}
 	return 0;
 }
@@ -653,7 +651,7 @@ int pilotPass(simcu_ *r, bool needOP, bool needTran)
 				b.S.reserve(std::max(1, p.stateDoubles) * m8) ||
 				b.IS.reserve(std::max(1, p.stateInts) * m4) || b.CD.reserve(CD_NUM * m8) ||
 				b.CI.reserve(CI_NUM * m4) || b.Ht.reserve(R * m8) ||
-				b.Hx.reserve((size_t)R * std::max(1, nh) * m8) || b.remaining.reserve(sizeof(int)))
+				b.Hx.reserve((size_t)R * (nh + 1) * m8) || b.remaining.reserve(sizeof(int)))
 			break;
 		if (cudaMemset(b.S.p, 0, std::max(1, p.stateDoubles) * m8) != cudaSuccess ||
 				cudaMemset(b.IS.p, 0, std::max(1, p.stateInts) * m4) != cudaSuccess)
@@ -861,7 +859,7 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		}
 	}
 	r->histRecords = R;
-	if (r->dHt.reserve((size_t)R * slots * 8) || r->dHx.reserve((size_t)R * nh * slots * 8)) return -1;
+	if (r->dHx.reserve((size_t)R * (nh + 1) * slots * 8)) return -1;
 	for (int ph = 0; ph < 2; ph++) {
 		SimcuArgs &a = r->args[ph];
 		a.histRecords = R;

@@ -28,7 +28,9 @@
 
 SIMCU_HD double calcDiv(double x, double y, double m)
 {
-	return (fabs(y) > m) ? (x / y) : ((y > 0) ? x / m : x / (-m));
+	/* parser.lem:30-31: x/y if |y| > m, else x/(+-m) - as ONE division */
+	const double den = (fabs(y) > m) ? y : ((y > 0) ? m : -m);
+	return x / den;
 }
 
 SIMCU_HD double calcLn(double x) { return log(fabs(x)); }

@@ -128,7 +128,21 @@ DEV const int *bvOf(const Inst &c, const int *d, const int *) { return c.a.bvar 
 /* ------------------------------------------------------------------------ *
  * Piecewise tables: libs/simulator/math/piecewise.c:44-67,96-104,226-263
  * ------------------------------------------------------------------------ */
-struct Table { const double *x, *y, *m; int len; int type; };
+/* A table is stored packed, one 32-byte entry per point: (x_i, y_i, m_i, x_{i+1})
+ * with m = slope (linear) or second derivative (cubic) and x_{i+1} = +inf for
+ * the last point - so the index walk and a linear lookup cost ONE read-only
+ * 32-byte fetch per visited point instead of a chain of dependent loads. */
+struct Table { const double *p; int len; int type; };
+struct TabEntry { double x, y, m, xn; };
+
+DEV TabEntry tabLoad(const Table &t, int i)
+{
+	const double2 a = __ldg(reinterpret_cast<const double2 *>(t.p + 4 * (size_t)i));
+	const double2 b = __ldg(reinterpret_cast<const double2 *>(t.p + 4 * (size_t)i) + 1);
+	TabEntry e;
+	e.x = a.x; e.y = a.y; e.m = b.x; e.xn = b.y;
+	return e;
+}
 
 DEV Table tableOf(const SimcuArgs &a, int t)
 {
@@ -136,51 +150,56 @@ DEV Table tableOf(const SimcuArgs &a, int t)
 	const int off = __ldg(&a.tabOff[t]);
 	r.len = __ldg(&a.tabOff[t + 1]) - off;
 	r.type = __ldg(&a.tabType[t]);
-	r.x = a.tabX + off; r.y = a.tabY + off; r.m = a.tabM + off;
+	r.p = a.tabP + 4 * (size_t)off;
 	return r;
 }
 
-/* the cached index only shortens the walk; the landing index depends on x0 */
-DEV int pwSetIndex(const Table &t, int index, double x0)
+/* piecewise.c:44-67.  The cached index only shortens the walk; the landing
+ * index depends on x0 alone.  Returns the entry at the landing index in e. */
+DEV int pwSetIndex(const Table &t, int index, double x0, TabEntry &e)
 {
 	if ((index < 0) || (index > t.len - 1)) index = 0;
+	e = tabLoad(t, index);
 	while ((index >= 0) && (index < t.len - 1)) {
-		if (__ldg(&t.x[index]) <= x0) {
+		if (e.x <= x0) {
 			if (index == t.len - 2) return index;
-			if (__ldg(&t.x[index + 1]) > x0) return index;
+			if (e.xn > x0) return index;
 			index++;
 		} else {
 			if (index == 0) return index;
 			index--;
 		}
+		e = tabLoad(t, index);
 	}
 	return index;
 }
 
 struct PwValue { double y, dydx; int index; };
 
-DEVFN PwValue pwCalcValueFn(const double *tx, const double *ty, const double *tm, int len,
-		int type, int index, double x0)
+/* piecewise.c:226-263 */
+DEVFN PwValue pwCalcValueFn(const double *tp, int len, int type, int index, double x0)
 {
 	Table t;
-	t.x = tx; t.y = ty; t.m = tm; t.len = len; t.type = type;
+	t.p = tp; t.len = len; t.type = type;
 	PwValue r;
-	index = pwSetIndex(t, index, x0);
+	TabEntry e;
+	index = pwSetIndex(t, index, x0, e);
 	r.index = index;
 	const int i = index;
 	if ((i == 0) || (i >= t.len - 2)) {
-		if (__ldg(&t.x[0]) > x0) { r.y = __ldg(&t.y[0]); r.dydx = 0; return r; }
-		if (__ldg(&t.x[t.len - 1]) < x0) { r.y = __ldg(&t.y[t.len - 1]); r.dydx = 0; return r; }
+		const TabEntry first = tabLoad(t, 0), last = tabLoad(t, t.len - 1);
+		if (first.x > x0) { r.y = first.y; r.dydx = 0; return r; }
+		if (last.x < x0) { r.y = last.y; r.dydx = 0; return r; }
 	}
 	if (t.type == 'l') {
-		const double mi = __ldg(&t.m[i]);
-		r.y = __ldg(&t.y[i]) + mi * (x0 - __ldg(&t.x[i]));
-		r.dydx = mi;
+		r.y = e.y + e.m * (x0 - e.x);
+		r.dydx = e.m;
 	} else {
-		const double xi = __ldg(&t.x[i]), yi = __ldg(&t.y[i]);
-		const double mi = __ldg(&t.m[i]), mi1 = __ldg(&t.m[i + 1]);
-		const double dx0 = x0 - xi, dy = __ldg(&t.y[i + 1]) - yi;
-		const double dx = __ldg(&t.x[i + 1]) - xi;
+		const TabEntry n = tabLoad(t, i + 1);
+		const double xi = e.x, yi = e.y;
+		const double mi = e.m, mi1 = n.m;
+		const double dx0 = x0 - xi, dy = n.y - yi;
+		const double dx = n.x - xi;
 		const double pa = dy / dx - dx * (mi1 + mi * 2.0) / 6.0;
 		const double pb = 0.5 * mi;
 		const double pc = (mi1 - mi) / (6.0 * dx);
@@ -192,16 +211,17 @@ DEVFN PwValue pwCalcValueFn(const double *tx, const double *ty, const double *tm
 
 DEV void pwCalcValue(const Table &t, int &index, double x0, double &y0, double &dydx0)
 {
-	const PwValue r = pwCalcValueFn(t.x, t.y, t.m, t.len, t.type, index, x0);
+	const PwValue r = pwCalcValueFn(t.p, t.len, t.type, index, x0);
 	index = r.index; y0 = r.y; dydx0 = r.dydx;
 }
 
 /* piecewise.c:204-222 with its two dead branches */
 DEV double pwGetNextX(const Table &t, int &index, double x0)
 {
-	index = pwSetIndex(t, index, x0);
+	TabEntry e;
+	index = pwSetIndex(t, index, x0, e);
 	if (index == t.len - 1) return HUGE_VAL;
-	return __ldg(&t.x[index + 1]);
+	return e.xn;
 }
 
 /* ------------------------------------------------------------------------ *
@@ -850,8 +870,8 @@ DEV void devInitStep(Inst &c, const int *d)
  * record r lives in slot r % R.  Returns false if the needed record is gone. */
 struct TlinePast { double v[6]; int hint; int ok; };
 
-DEVFN TlinePast tlinePastFn(const double *Ht, const double *Hx, int R, int nh, size_t hstride,
-		int hslot, int count, int hint, double tp, int c0, int c1, int c2, int c3, int c4, int c5)
+DEVFN TlinePast tlinePastFn(const double *Hx, int R, int nh, int hslot, int count, int hint,
+		double tp, int c0, int c1, int c2, int c3, int c4, int c5)
 {
 	TlinePast r;
 	r.ok = 0; r.hint = hint;
@@ -860,7 +880,9 @@ DEVFN TlinePast tlinePastFn(const double *Ht, const double *Hx, int R, int nh, s
 	const int lo = (count > R) ? count - R : 0;
 	int i = hint;
 	if (i < lo || i >= count) i = lo;
-	#define HT(q) Ht[(size_t)((q) % R) * hstride + hslot]
+	/* this thread's ring: R records of (time, nh values), contiguous per record */
+	const double *ring = Hx + (size_t)hslot * R * (nh + 1);
+	#define HT(q) ring[(size_t)((q) % R) * (nh + 1)]
 	while (HT(i) > tp && i > lo) i--;
 	if (HT(i) > tp) return r;                 /* fell off the ring */
 	while (i + 1 < count && HT(i + 1) <= tp) i++;
@@ -868,14 +890,15 @@ DEVFN TlinePast tlinePastFn(const double *Ht, const double *Hx, int R, int nh, s
 	int iP, iN;
 	if (i + 1 < count) { iP = i; iN = i + 1; }
 	else { if (i - 1 < lo) return r; iP = i - 1; iN = i; }
-	const double tP = HT(iP), tN = HT(iN);
+	const double *recP = &HT(iP), *recN = &HT(iN);
 	#undef HT
+	const double tP = recP[0], tN = recN[0];
 	const int cols[6] = {c0, c1, c2, c3, c4, c5};
 	#pragma unroll
 	for (int j = 0; j < 6; j++) {
 		if (cols[j] < 0) continue;
-		const double xP = Hx[((size_t)(iP % R) * nh + cols[j]) * hstride + hslot];
-		const double xN = Hx[((size_t)(iN % R) * nh + cols[j]) * hstride + hslot];
+		const double xP = recP[1 + cols[j]];
+		const double xN = recN[1 + cols[j]];
 		r.v[j] = ((xN - xP) / (tN - tP)) * (tp - tP) + xP;
 	}
 	r.ok = 1;
@@ -915,8 +938,8 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 			Vk = c.S(sb + 2); Vj = c.S(sb + 3); Vl = c.S(sb + 4); Vm = c.S(sb + 5);
 		} else {
 			const int *h = d + DF_TH0;              /* R S K J L M */
-			const TlinePast r = tlinePastFn(c.a.Ht, c.a.Hx, c.a.histRecords, c.a.nh, c.hstride,
-					c.hslot, c.hcount, c.IS(ib + 2), tp, h[0], h[1], h[2], h[3], h[4], h[5]);
+			const TlinePast r = tlinePastFn(c.a.Hx, c.a.histRecords, c.a.nh, c.hslot, c.hcount,
+					c.IS(ib + 2), tp, h[0], h[1], h[2], h[3], h[4], h[5]);
 			if (!r.ok) { c.err = SIMCU_ERR_HISTORY; return 0; }
 			c.IS(ib + 2) = r.hint;
 			Ir = r.v[0]; Is = r.v[1]; Vk = r.v[2]; Vj = r.v[3]; Vl = r.v[4]; Vm = r.v[5];
@@ -1133,11 +1156,10 @@ DEV void recordStep(Inst &c, const int *rows, double tNow)
 {
 	const SimcuArgs &a = c.a;
 	if (a.nh > 0 && a.histRecords > 0) {
-		const int slot = c.hcount % a.histRecords;
-		a.Ht[(size_t)slot * c.hstride + c.hslot] = tNow;
+		double *rec = a.Hx + ((size_t)c.hslot * a.histRecords + c.hcount % a.histRecords) * (a.nh + 1);
+		rec[0] = tNow;
 		SIMCU_UNROLL
-		for (int j = 0; j < SIMCU_NH_LOOP; j++)
-			a.Hx[((size_t)slot * a.nh + j) * c.hstride + c.hslot] = c.X(LDI(&rows[j]));
+		for (int j = 0; j < SIMCU_NH_LOOP; j++) rec[1 + j] = c.X(LDI(&rows[j]));
 		c.hcount++;
 	}
 	if (a.rawMaxPoints > 0 && c.i >= a.rawFirst && c.i < a.rawFirst + a.rawCount) {

@@ -468,10 +468,11 @@ struct Flattener {
 			for (int i = last - 1; i > 0; i--) m[i] = (v[i] - h[i] * m[i + 1]) / u[i];
 		}
 		p.tabType.push_back(type);
-		p.tabX.insert(p.tabX.end(), x.begin(), x.end());
-		p.tabY.insert(p.tabY.end(), y.begin(), y.end());
-		p.tabM.insert(p.tabM.end(), m.begin(), m.end());
-		p.tabOff.push_back((int)p.tabX.size());
+		for (int i = 0; i < n; i++) {
+			p.tabP.push_back(x[i]); p.tabP.push_back(y[i]); p.tabP.push_back(m[i]);
+			p.tabP.push_back((i + 1 < n) ? x[i + 1] : HUGE_VAL);
+		}
+		p.tabOff.push_back((int)p.tabP.size() / 4);
 		return true;
 	}
 
@@ -481,7 +482,7 @@ struct Flattener {
 		p.pmap.clear(); p.pconst.clear(); p.pinst.clear(); p.iinst.clear();
 		p.ninst = 0; p.niinst = 0;
 		p.tabOff.assign(1, 0); p.tabType.clear();
-		p.tabX.clear(); p.tabY.clear(); p.tabM.clear();
+		p.tabP.clear();
 		for (size_t k = 0; k < nl.devs.size(); k++) {
 			const Dev &d = nl.devs[k];
 			int *rec = writeRecords ? &p.dev[k * SIMCU_DEV_STRIDE] : nullptr;

@@ -76,7 +76,7 @@ struct Program {
 	std::vector<int> calcOff, calcCode, calcVarOff, calcVars;
 	std::vector<double> calcConst;
 	std::vector<int> tabOff, tabType;
-	std::vector<double> tabX, tabY, tabM;
+	std::vector<double> tabP;                     /* [point][4] = x, y, m, x_next */
 	std::vector<int> histRows;
 	std::vector<int> pmap; std::vector<double> pconst;
 	std::vector<double> pinst;                    /* [ninst][M] */

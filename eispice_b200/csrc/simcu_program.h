@@ -119,7 +119,7 @@ typedef struct {
 	const int *calcVars;      /* row index (0 = ground), CALC_VAR_TIME */
 	const int *tabOff;        /* [ntab+1] */
 	const int *tabType;       /* 'l' / 'c' */
-	const double *tabX, *tabY, *tabM;
+	const double *tabP;       /* packed tables: [point][4] = x, y, m, x_next */
 	const int *histRows;      /* [nh] row index (1-based) recorded per step */
 	int nh, histRecords;
 	const int *probeRows;     /* [nprobes] row index (1-based) */
@@ -134,7 +134,7 @@ typedef struct {
 	/* per-instance state, all [slot][M] */
 	double *A, *B, *X, *Xrec, *S, *CD;
 	int *IS, *CI;
-	double *Ht, *Hx;          /* history ring: [R][M], [R][nh][M] */
+	double *Ht, *Hx;          /* T-line history: Hx[thread][R][1 + nh], column 0 = time */
 	double *outGrid;          /* [ngrid][nprobes][M] */
 	double *outRaw;           /* [rawMaxPoints][N+1][rawCount] */
 	double *wsGlobal;         /* [(F+N)][M] when the workspace is not in smem */
