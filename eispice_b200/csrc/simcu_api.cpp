@@ -103,6 +103,7 @@ struct _simcu {
 	int interpreter = 0;            /* 1: run the batch on the generic kernels */
 	int minBlocks = 0;              /* __launch_bounds__ second argument */
 	int maxBlocksPerSM = 0;         /* cap on resident blocks (0 = occupancy limit) */
+	int minBlocksUsed = 0, jitMinBlocks = -1;
 	std::vector<char> active[2];
 	std::shared_ptr<JitKernel> jit;
 	std::vector<int> jitProbes;
@@ -693,9 +694,11 @@ std::map<std::string, std::shared_ptr<JitKernel> > gKernelCache;
 
 int buildJitKernel(simcu_ *r)
 {
-	if (r->jit && r->jitProbes == r->probeRows && r->jitTpb == r->tpb) return 0;
+	if (r->jit && r->jitProbes == r->probeRows && r->jitTpb == r->tpb &&
+			r->jitMinBlocks == r->minBlocksUsed)
+		return 0;
 	const std::string src = assembleSource(r->prog, r->sched, r->active, r->probeRows, r->tpb,
-			r->minBlocks);
+			r->minBlocksUsed);
 	const std::string &key = src;
 	std::map<std::string, std::shared_ptr<JitKernel> >::iterator it = gKernelCache.find(key);
 	if (it != gKernelCache.end()) r->jit = it->second;
@@ -708,7 +711,7 @@ int buildJitKernel(simcu_ *r)
 		r->jit = k;
 		r->stats.jitCompiles++;
 	}
-	r->jitProbes = r->probeRows; r->jitTpb = r->tpb;
+	r->jitProbes = r->probeRows; r->jitTpb = r->tpb; r->jitMinBlocks = r->minBlocksUsed;
 	return 0;
 }
 
@@ -802,6 +805,9 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 	}
 	if (uploadParameters(r, 0)) return -1;
 	if (uploadSchedule(r, 0) || uploadSchedule(r, 1)) return -1;
+	int sms = 148, dev = 0;
+	CU(cudaGetDevice(&dev));
+	CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
 	/* symbolic analysis on the pilot batch (one-off per topology and time scale) */
 	const bool needOP = r->sched[0].lu.empty() || !r->forcePc[0].empty();
@@ -812,9 +818,6 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		if (uploadSchedule(r, 1)) return -1;
 	}
 
-	int sms = 148, dev = 0;
-	CU(cudaGetDevice(&dev));
-	CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 	int slots = M;
 	if (r->interpreter) {
 		/* whole batch on the generic kernels: per-instance state in HBM */
@@ -826,6 +829,13 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 	} else {
 		r->tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
 		r->wsShared = 0;
+		/* Register budget (measured on B200): a batch that fits the machine at
+		 * 255 registers per thread is latency-bound and wants them all; a larger
+		 * batch of a SMALL circuit gains more from twice the resident warps
+		 * (128 registers); mid-size circuits (IBIS links) spill too much there. */
+		r->minBlocksUsed = r->minBlocks;
+		if (r->minBlocks == 0 && p.N <= 12 && (long long)M > (long long)sms * 4 * r->tpb)
+			r->minBlocksUsed = 65536 / (128 * r->tpb);
 		if (buildJitKernel(r)) return -1;
 		/* active lanes per warp */
 		const int wpb = r->tpb / 32;

@@ -16,7 +16,10 @@
  * outgrows the instruction cache (measured: stall_no_inst was the top stall). */
 #define DEVFN __device__ __noinline__
 
-DEVFN double simcuAtan2(double y, double x) { return atan2(y, x); }
+DEVFN double simcuAtan2Fn(double y, double x) { return atan2(y, x); }
+/* atan2(+-0, x > 0) is +-0 exactly (C99 F.9.1.4): the break-point test of a
+ * signal that did not move - the common case - needs no call */
+DEV double simcuAtan2(double y, double x) { return (y == 0.0 && x > 0.0) ? y : simcuAtan2Fn(y, x); }
 DEVFN double simcuExp(double x) { return exp(x); }
 
 #define MaxAbs(x, y) ((fabs(x) > fabs(y)) ? fabs(x) : fabs(y))
@@ -747,6 +750,8 @@ DEV void devLoad(Inst &c, const int *d, const int *bv = nullptr)
 		c.Aset(s[6], 1.0); c.Aset(s[7], -1.0); c.Aset(s[8], 1.0); c.Aset(s[9], -1.0);
 		const double z0 = c.P(d[DF_PZ0]);
 		c.Aplus(s[12], -z0); c.Aplus(s[13], -z0);
+		const double loss = c.P(d[DF_PLOSS]);
+		c.S(sb + 24) = (loss == HUGE_VAL) ? 1.0 : simcuExp(-loss / 2);
 		break;
 	}
 	case DK_VI: {                               /* vicurve.c:167-221 */
@@ -868,41 +873,46 @@ DEV void devInitStep(Inst &c, const int *d)
 /* T-line delayed lookup: history_interp.c:42-92, history.c:36-59.  Records
  * are kept in a ring of a.histRecords entries; `count` records exist so far,
  * record r lives in slot r % R.  Returns false if the needed record is gone. */
-struct TlinePast { double v[6]; int hint; int ok; };
-
-DEVFN TlinePast tlinePastFn(const double *Hx, int R, int nh, int hslot, int count, int hint,
-		double tp, int c0, int c1, int c2, int c3, int c4, int c5)
+/* Finds the two history records that bracket (or, past the newest record,
+ * precede) the delayed time tp.  ring = this thread's records, `rec` doubles
+ * each, column 0 = time; record q lives at position q % R.  Returns
+ * (hint, position of the earlier record, position of the later one, ok).
+ * One modulo per call; positions wrap by comparison while walking. */
+DEVFN int4 tlineLocateFn(const double *ring, int R, int rec, int count, int hint, double tp)
 {
-	TlinePast r;
-	r.ok = 0; r.hint = hint;
-	#pragma unroll
-	for (int j = 0; j < 6; j++) r.v[j] = 0.0;
+	int4 r;
+	r.x = hint; r.y = 0; r.z = 0; r.w = 0;
 	const int lo = (count > R) ? count - R : 0;
 	int i = hint;
 	if (i < lo || i >= count) i = lo;
-	/* this thread's ring: R records of (time, nh values), contiguous per record */
-	const double *ring = Hx + (size_t)hslot * R * (nh + 1);
-	#define HT(q) ring[(size_t)((q) % R) * (nh + 1)]
-	while (HT(i) > tp && i > lo) i--;
-	if (HT(i) > tp) return r;                 /* fell off the ring */
-	while (i + 1 < count && HT(i + 1) <= tp) i++;
-	r.hint = i;
-	int iP, iN;
-	if (i + 1 < count) { iP = i; iN = i + 1; }
-	else { if (i - 1 < lo) return r; iP = i - 1; iN = i; }
-	const double *recP = &HT(iP), *recN = &HT(iN);
-	#undef HT
-	const double tP = recP[0], tN = recN[0];
-	const int cols[6] = {c0, c1, c2, c3, c4, c5};
-	#pragma unroll
-	for (int j = 0; j < 6; j++) {
-		if (cols[j] < 0) continue;
-		const double xP = recP[1 + cols[j]];
-		const double xN = recN[1 + cols[j]];
-		r.v[j] = ((xN - xP) / (tN - tP)) * (tp - tP) + xP;
+	int pos = i % R;
+	double ti = ring[(size_t)pos * rec];
+	while (ti > tp && i > lo) {
+		i--; pos = (pos == 0) ? R - 1 : pos - 1;
+		ti = ring[(size_t)pos * rec];
 	}
-	r.ok = 1;
+	if (ti > tp) return r;                    /* fell off the ring */
+	int pn = (pos + 1 == R) ? 0 : pos + 1;
+	while (i + 1 < count) {
+		const double tn = ring[(size_t)pn * rec];
+		if (!(tn <= tp)) break;
+		i++; pos = pn; pn = (pos + 1 == R) ? 0 : pos + 1;
+	}
+	r.x = i;
+	if (i + 1 < count) { r.y = pos; r.z = pn; }
+	else {                                    /* extrapolate from the last two */
+		if (i - 1 < lo) return r;
+		r.y = (pos == 0) ? R - 1 : pos - 1; r.z = pos;
+	}
+	r.w = 1;
 	return r;
+}
+
+DEV double tlineInterp(const double *recP, const double *recN, int col, double tP, double tN, double tp)
+{
+	if (col < 0) return 0.0;
+	const double xP = recP[1 + col], xN = recN[1 + col];
+	return ((xN - xP) / (tN - tP)) * (tp - tP) + xP;
 }
 
 DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
@@ -938,11 +948,16 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 			Vk = c.S(sb + 2); Vj = c.S(sb + 3); Vl = c.S(sb + 4); Vm = c.S(sb + 5);
 		} else {
 			const int *h = d + DF_TH0;              /* R S K J L M */
-			const TlinePast r = tlinePastFn(c.a.Hx, c.a.histRecords, c.a.nh, c.hslot, c.hcount,
-					c.IS(ib + 2), tp, h[0], h[1], h[2], h[3], h[4], h[5]);
-			if (!r.ok) { c.err = SIMCU_ERR_HISTORY; return 0; }
-			c.IS(ib + 2) = r.hint;
-			Ir = r.v[0]; Is = r.v[1]; Vk = r.v[2]; Vj = r.v[3]; Vl = r.v[4]; Vm = r.v[5];
+			const int rec = c.a.nh + 1;
+			const double *ring = c.a.Hx + (size_t)c.hslot * c.a.histRecords * rec;
+			const int4 r = tlineLocateFn(ring, c.a.histRecords, rec, c.hcount, c.IS(ib + 2), tp);
+			if (!r.w) { c.err = SIMCU_ERR_HISTORY; return 0; }
+			c.IS(ib + 2) = r.x;
+			const double *recP = ring + (size_t)r.y * rec, *recN = ring + (size_t)r.z * rec;
+			const double tP = recP[0], tN = recN[0];
+			Ir = tlineInterp(recP, recN, h[0], tP, tN, tp); Is = tlineInterp(recP, recN, h[1], tP, tN, tp);
+			Vk = tlineInterp(recP, recN, h[2], tP, tN, tp); Vj = tlineInterp(recP, recN, h[3], tP, tN, tp);
+			Vl = tlineInterp(recP, recN, h[4], tP, tN, tp); Vm = tlineInterp(recP, recN, h[5], tP, tN, tp);
 		}
 		const double z0 = c.P(d[DF_PZ0]), loss = c.P(d[DF_PLOSS]);
 		double Vr, Vs;
@@ -950,8 +965,9 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 			Vr = (Vl - Vm) + z0 * Is;
 			Vs = (Vk - Vj) + z0 * Ir;
 		} else {
-			Vr = simcuExp(-loss / 2) * ((Vl - Vm) + z0 * Is);
-			Vs = simcuExp(-loss / 2) * ((Vk - Vj) + z0 * Ir);
+			/* exp(-loss/2), evaluated once per run at load (same value) */
+			Vr = c.S(sb + 24) * ((Vl - Vm) + z0 * Is);
+			Vs = c.S(sb + 24) * ((Vk - Vj) + z0 * Ir);
 		}
 		c.Bplus(d[DF_ROWR], Vr - c.S(sb)); c.S(sb) = Vr;
 		c.Bplus(d[DF_ROWS], Vs - c.S(sb + 1)); c.S(sb + 1) = Vs;

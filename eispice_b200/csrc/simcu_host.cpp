@@ -634,7 +634,7 @@ struct Flattener {
 				}
 				const int rows[6] = {R, S, K, J, L, Mm};
 				for (int j = 0; j < 6; j++) rec[DF_TH0 + j] = rows[j] ? histCol[rows[j]] : -1;
-				sbase += 6 + 2 * CB_DOUBLES; ibase += 3;
+				sbase += 6 + 2 * CB_DOUBLES + 1; ibase += 3;
 				break;
 			}
 			case DK_VI: {                      /* vicurve.c:333-356 */

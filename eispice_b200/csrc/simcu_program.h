@@ -61,7 +61,7 @@ enum {
 #define CB_DOUBLES 9      /* x[3] t[3] theta[3] */
 /* C / L : G Ieq integ          ints: n                */
 /* V / I : dc cb pwdc           ints: cb.n pwIndex     */
-/* T     : Vr Vs icK icJ icL icM cbR cbS   ints: cbR.n cbS.n hint */
+/* T     : Vr Vs icK icJ icL icM cbR cbS att ints: cbR.n cbS.n hint */
 /* VI    : G Ieq a lastV cb     ints: clState cb.n viIndex taIndex */
 /* BI/BV : Ic In Beq lastV cb G[nbv]       ints: clState cb.n */
 /* BC    : G Ieq integ Ic Cn Ceq lastV R[nbv]   ints: n clState */
