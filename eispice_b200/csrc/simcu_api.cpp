@@ -104,6 +104,7 @@ struct _simcu {
 	int minBlocks = 0;              /* __launch_bounds__ second argument */
 	int maxBlocksPerSM = 0;         /* cap on resident blocks (0 = occupancy limit) */
 	int minBlocksUsed = 0, jitMinBlocks = -1;
+	double jitGmin = -1.0;
 	std::vector<char> active[2];
 	std::shared_ptr<JitKernel> jit;
 	std::vector<int> jitProbes;
@@ -695,10 +696,10 @@ std::map<std::string, std::shared_ptr<JitKernel> > gKernelCache;
 int buildJitKernel(simcu_ *r)
 {
 	if (r->jit && r->jitProbes == r->probeRows && r->jitTpb == r->tpb &&
-			r->jitMinBlocks == r->minBlocksUsed)
+			r->jitMinBlocks == r->minBlocksUsed && r->jitGmin == r->ctl.gmin)
 		return 0;
 	const std::string src = assembleSource(r->prog, r->sched, r->active, r->probeRows, r->tpb,
-			r->minBlocksUsed);
+			r->minBlocksUsed, r->ctl.gmin);
 	const std::string &key = src;
 	std::map<std::string, std::shared_ptr<JitKernel> >::iterator it = gKernelCache.find(key);
 	if (it != gKernelCache.end()) r->jit = it->second;
@@ -711,7 +712,7 @@ int buildJitKernel(simcu_ *r)
 		r->jit = k;
 		r->stats.jitCompiles++;
 	}
-	r->jitProbes = r->probeRows; r->jitTpb = r->tpb; r->jitMinBlocks = r->minBlocksUsed;
+	r->jitProbes = r->probeRows; r->jitTpb = r->tpb; r->jitMinBlocks = r->minBlocksUsed; r->jitGmin = r->ctl.gmin;
 	return 0;
 }
 
@@ -932,6 +933,7 @@ int collectStats(simcu_ *r)
 	CU(cudaMemcpy(ci.data(), r->dCI.p, ci.size() * sizeof(int), cudaMemcpyDeviceToHost));
 	simcuStats_ &s = r->stats;
 	s.accepted = s.rejectedLTE = s.rejectedNC = s.factorizations = s.opFactorizations = s.failed = 0;
+	s.pivotBreakdowns = 0;
 	for (int i = 0; i < M; i++) {
 		s.accepted += ci[(size_t)CI_ACCEPTED * M + i];
 		s.rejectedLTE += ci[(size_t)CI_REJ_LTE * M + i];
@@ -939,6 +941,7 @@ int collectStats(simcu_ *r)
 		s.factorizations += ci[(size_t)CI_NFACT * M + i];
 		s.opFactorizations += ci[(size_t)CI_NFACT_OP * M + i];
 		s.failed += (ci[(size_t)CI_STATUS * M + i] != 0);
+		if (!r->interpreter) s.pivotBreakdowns += ci[(size_t)CI_BREAK * M + i];
 	}
 	const Program &p = r->prog;
 	s.numUnknowns = p.N; s.numNonzeros = p.nnzA;
@@ -1083,7 +1086,8 @@ int simcuFetchCounters(simcu_ *r, char *which, int *out)
 	if (!r || !r->ran || !which || !out) return -1;
 	static const struct { const char *name; int row; } rows[] = {
 		{"status", CI_STATUS}, {"accepted", CI_ACCEPTED}, {"rejected_lte", CI_REJ_LTE},
-		{"rejected_nc", CI_REJ_NC}, {"factorizations", CI_NFACT}, {"op_factorizations", CI_NFACT_OP}};
+		{"rejected_nc", CI_REJ_NC}, {"factorizations", CI_NFACT}, {"op_factorizations", CI_NFACT_OP},
+		{"pivot_breakdowns", CI_BREAK}};
 	for (size_t i = 0; i < sizeof rows / sizeof rows[0]; i++)
 		if (!std::strcmp(which, rows[i].name)) {
 			CU(cudaMemcpy(out, r->dCI.as<int>() + (size_t)rows[i].row * r->M, (size_t)r->M * 4,
@@ -1200,7 +1204,7 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 			return fail("%s", err.c_str());
 	}
 	const int tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
-	const std::string src = assembleSource(p, sched, active, probeRows, tpb, r->minBlocks);
+	const std::string src = assembleSource(p, sched, active, probeRows, tpb, r->minBlocks, r->ctl.gmin);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;
 	std::string err;

@@ -195,7 +195,9 @@ void emitCalc(Out &o, const Program &p, int id, int dvar, const char *ind)
 void emitCalcAll(Out &o, const Program &p)
 {
 	o.f("DEV void genCalc(Inst &c, int id, int dvar, double &f, double &dv)\n{\n");
-	o.f("\tconst double m = c.a.ctl.gmin;\n\t(void)m;\n\tf = 0.0; dv = 0.0;\n\tswitch (id) {\n");
+	/* gmin (the guard of every division, parser.lem:30-31) is a compile-time
+	 * constant here, so divisions of constants by constants fold away */
+	o.f("\tconst double m = SIMCU_GMIN;\n\t(void)m; (void)c;\n\tf = 0.0; dv = 0.0;\n\tswitch (id) {\n");
 	const int ncalc = (int)p.calcOff.size() - 1;
 	for (int id = 0; id < ncalc; id++) {
 		const int v0 = p.calcVarOff[id], v1 = p.calcVarOff[id + 1];
@@ -272,6 +274,7 @@ void emitPhases(Out &o, const Program &p)
 		"\treturn linear;\n}\n\n", "}\n\n", "}\n\n"};
 	for (int ph = 0; ph < 7; ph++) {
 		o.f("%s", head[ph]);
+
 		for (int k = 0; k < p.ndev; k++) {
 			if (!inPhase(&p.dev[(size_t)k * SIMCU_DEV_STRIDE], ph)) continue;
 			emitRecord(o, p, k);
@@ -351,7 +354,8 @@ void emitRows(Out &o, const char *name, const std::vector<int> &rows)
 
 }  /* namespace */
 
-std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock, int minBlocks)
+std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock, int minBlocks,
+		double gmin)
 {
 	Out o;
 	o.f("#define SIMCU_JIT 1\n");
@@ -362,6 +366,7 @@ std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock
 	o.f("#define SIMCU_NPROBES %d\n#define SIMCU_TPB %d\n#define SIMCU_MINB %d\n", numProbes,
 			threadsPerBlock, minBlocks > 0 ? minBlocks : 1);
 	o.f("#define HUGE_VAL (__longlong_as_double(0x7ff0000000000000LL))\n");
+	o.f("#define SIMCU_GMIN (%s)\n", lit(gmin).c_str());
 	o.f("#define M_PI 3.14159265358979323846\n");
 	o.f("enum { SIMCU_OK = %d, SIMCU_ERR_TIMESTEP = %d, SIMCU_ERR_SINGULAR = %d, SIMCU_ERR_NAN = %d,\n"
 			"\tSIMCU_ERR_OP = %d, SIMCU_ERR_HISTORY = %d, SIMCU_ERR_BUDGET = %d };\n\n",

@@ -13,14 +13,15 @@
 namespace simcu {
 
 /* #defines of the topology's sizes; first part of the translation unit */
-std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock, int minBlocks);
+std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock, int minBlocks,
+		double gmin);
 /* device records, expressions and the unrolled LU of both phases */
 std::string generateTopology(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<int> &probeRows);
 /* prelude + embedded library headers + topology + kernel */
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<int> &probeRows,
-		int threadsPerBlock, int minBlocks);
+		int threadsPerBlock, int minBlocks, double gmin);
 
 /* A compiled kernel.  compile() needs no GPU (NVRTC only); load() does. */
 struct JitKernel {

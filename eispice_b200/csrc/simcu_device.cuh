@@ -875,8 +875,9 @@ DEV void devInitStep(Inst &c, const int *d)
  * record r lives in slot r % R.  Returns false if the needed record is gone. */
 /* Finds the two history records that bracket (or, past the newest record,
  * precede) the delayed time tp.  ring = this thread's records, `rec` doubles
- * each, column 0 = time; record q lives at position q % R.  Returns
- * (hint, position of the earlier record, position of the later one, ok).
+ * each, column 0 = time; record q lives at position q % R.  Returns (hint,
+ * position of the earlier record, position of the later one, position of the
+ * hint record + 1 or 0 = the needed record is gone).
  * One modulo per call; positions wrap by comparison while walking. */
 DEVFN int4 tlineLocateFn(const double *ring, int R, int rec, int count, int hint, double tp)
 {
@@ -904,7 +905,7 @@ DEVFN int4 tlineLocateFn(const double *ring, int R, int rec, int count, int hint
 		if (i - 1 < lo) return r;
 		r.y = (pos == 0) ? R - 1 : pos - 1; r.z = pos;
 	}
-	r.w = 1;
+	r.w = pos + 1;                            /* ring position of record `hint`, + 1 */
 	return r;
 }
 

@@ -78,9 +78,9 @@ void jitSetNvrtcPath(const char *path) { gNvrtcHint = path ? path : ""; }
 
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<int> &probeRows,
-		int threadsPerBlock, int minBlocks)
+		int threadsPerBlock, int minBlocks, double gmin)
 {
-	std::string s = generatePrelude(p, (int)probeRows.size(), threadsPerBlock, minBlocks);
+	std::string s = generatePrelude(p, (int)probeRows.size(), threadsPerBlock, minBlocks, gmin);
 	s += kSrcProgram;
 	s += kSrcCalc;
 	s += kSrcDevice;

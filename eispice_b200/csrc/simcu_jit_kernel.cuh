@@ -46,7 +46,7 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 
 	double time = 0.0, prevTime = 0.0, thisStep = 0.0, maxStep = 0.0, lteStep = 0.0;
 	int order = 1, brk = 0;
-	int nfact = 0, nfactOp = 0, accepted = 0, rejLte = 0, rejNc = 0;
+	int nfact = 0, nfactOp = 0, accepted = 0, rejLte = 0, rejNc = 0, pivotBreaks = 0;
 	long long attempts = 0;
 	bool transient = false;      /* false: the operating-point solve */
 
@@ -74,6 +74,13 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 		for (;;) {
 			if (transient) { genFactorSolve1(c); nfact++; }
 			else { genFactorSolve0(c); nfactOp++; }
+			/* pivot breakdown in a transient attempt (the fixed sequence met a
+			 * zero / non-finite pivot): reject the attempt as non-convergent, so
+			 * the step is cut and Newton restarts - per instance, on device */
+			if (transient && c.err == SIMCU_ERR_SINGULAR) {
+				c.err = 0; count = limit; pivotBreaks++;
+				break;
+			}
 			if (c.err) break;
 			if (count++ >= limit) break;
 			const int linear = genLinearize(c);
@@ -142,6 +149,7 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 	ci[(size_t)CI_NFACT * M] = nfact;
 	ci[(size_t)CI_NFACT_OP * M] = nfactOp;
 	ci[(size_t)CI_NPTS * M] = c.npts;
+	ci[(size_t)CI_BREAK * M] = pivotBreaks;
 }
 
 extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKernel(const SimcuArgs a, int opOnly)

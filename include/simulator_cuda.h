@@ -67,6 +67,7 @@ typedef struct {
 	int localBytesPerThread;
 	int gridBlocks;
 	int lanesPerWarp;          /* instances per warp of the specialised kernel */
+	long long pivotBreakdowns; /* transient attempts rejected for a zero pivot */
 } simcuStats_;
 
 /* simulatorNew (simulator.h:33): r must be NULL */

@@ -409,6 +409,39 @@ GOLDEN_COLUMNS = {
 }
 
 
+# ---- circuits without committed reference waveforms: pinned through the live
+# reference in the build container (tests/test_oracle_golden.py) and compared
+# oracle <-> GPU on the GPU box ------------------------------------------------
+def vi_spline_ta():
+    """VI device with a cubic-spline V-I table and a time-dependent multiplier
+    (math/piecewise.c:108-181, devices/vicurve.c:85-106), behind an RC."""
+    cct = _new("VI spline + TA")
+    vi = np.array([[-2, -0.08], [-1, -0.02], [0, 0.0], [0.5, 0.004], [1, 0.012],
+                   [2, 0.05], [3, 0.06]], dtype=float)
+    ta = np.array([[0, 0.0], [2e-9, 0.0], [3e-9, 1.0], [7e-9, 1.0], [8e-9, 0.3], [20e-9, 0.3]])
+    cct.Vx = eispice.V(1, 0, 0, eispice.Pulse(0, 2.5, '1n', '1n', '1n', '6n', '20n'))
+    cct.Rs = eispice.R(1, 2, 25)
+    cct.Cl = eispice.C(2, 0, '2p')
+    cct.VIx = eispice.VI(2, 0, eispice.PWC(vi), eispice.PWL(ta))
+    return cct
+
+
+def pwl_current_into_rlc():
+    """PWL current source into a parallel RLC (source_i.c, inductor.c, capacitor.c)."""
+    cct = _new("PWL I into RLC")
+    cct.Ix = eispice.I(1, 0, 0, eispice.PWL([[0, 0], ['1n', '1m'], ['3n', '-1m'], ['6n', 0]]))
+    cct.Rp = eispice.R(1, 0, 200)
+    cct.Lp = eispice.L(1, 0, '20n')
+    cct.Cp = eispice.C(1, 0, '5p')
+    return cct
+
+
+EXTRA_CASES = {
+    "vi_spline_ta": (vi_spline_ta, ('tran', '0.05n', '12n'), []),
+    "pwl_current_into_rlc": (pwl_current_into_rlc, ('tran', '0.02n', '10n'), []),
+}
+
+
 def all_cases():
     out = dict(CASES)
     out.update(IBIS_CASES)

@@ -281,3 +281,58 @@ def test_specialised_kernel_equals_generic_kernels(cfg, M):
     assert same >= need, "%d of %d instances share the step sequence" % (same, w.M)
     jit.close()
     gen.close()
+
+
+def test_pivot_breakdown_cuts_the_step_and_flags_only_that_instance():
+    """The fixed pivot sequence is chosen on pilot instances.  An instance whose
+    pivot turns out to be exactly zero (here L = 0 under a sequence that pivots
+    on the inductor's 2L/h entry) is handled on device: the attempt is rejected,
+    the step cut and Newton restarted; when that cannot help, the instance is
+    flagged 'timestep too small' and the rest of the batch is unaffected.
+    (The reference re-pivots on every factorisation and would survive L = 0.)"""
+    import eispice_b200 as eispice
+    cct = circuits._new("RL")
+    cct.V1 = eispice.V('a', 0, 0, eispice.Pulse(0, 1, '1n', '0.1n', '0.1n', '4n', '10n'))
+    cct.R1 = eispice.R('a', 'b', 50)
+    cct.L1 = eispice.L('b', 0, '1u')
+    M = 40
+    L = np.full(M, 1e-6)
+    L[7] = 0.0
+    eng = engine.Engine(cct.netlist(), M)
+    eng.set_option("num_pilots", 2)            # pilots = instances 0 and 39, both healthy
+    res = eng.tran_batch(0.01e-9, 10e-9, 0.0, {"L1.L": L}, ["v(b)", "i(L1)"])
+    pc, pr = eng.pivots(1)
+    names = eng.variables()[1:]
+    piv = {names[c]: names[r] for c, r in zip(pc, pr)}
+    assert piv["i(L1)"] == "i(L1)", "test premise: the sequence pivots on the 2L/h entry"
+    ok = np.ones(M, bool)
+    ok[7] = False
+    assert (res.status[ok] == 0).all()
+    assert res.status[7] == 1                  # SIMCU_ERR_TIMESTEP after repeated step cuts
+    assert res.stats["pivotBreakdowns"] >= 5 and res.stats["failed"] == 1
+    assert eng.counters("pivot_breakdowns")[7] == res.stats["pivotBreakdowns"]
+    assert np.isfinite(res.data[ok]).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("name", sorted(circuits.EXTRA_CASES))
+def test_extra_circuits_match_the_oracle(name):
+    """Cubic-spline VI table with a time-dependent multiplier, PWL current source:
+    the oracle is pinned to the live reference for these in the build container
+    (tests/test_oracle_golden.py); here the CUDA path is held to the oracle."""
+    build, an, _ = circuits.EXTRA_CASES[name]
+    nl = build().netlist()
+    eng = engine.Engine(nl, 1)
+    a = [units.float(x) for x in an[1:]]
+    data, var = eng.tran_single(*a)
+    ora = backends.OracleSim(nl)
+    for ph in (0, 1):
+        ora.set_pivots(ph, *eng.pivots(ph))
+    od, ov = ora.tran(*a)
+    assert var == ov
+    data, od = parity.drop_degenerate(data, a[0]), parity.drop_degenerate(od, a[0])
+    assert parity.grid_error(data[:, 0], data, od[:, 0], od, var, a[0], a[1]) < 1.0
+    assert data.shape == od.shape
+    frac, worst = parity.tight_fraction(data, od)
+    assert frac >= MIN_TIGHT_FRACTION, (frac, worst)
+    eng.close()

@@ -86,6 +86,20 @@ def test_oracle_matches_live_reference(name):
     assert frac >= MIN_TIGHT_FRACTION, (frac, worst)
 
 
+@pytest.mark.skipif(not backends.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", sorted(circuits.EXTRA_CASES))
+def test_oracle_matches_live_reference_extra(name):
+    build, an, _ = circuits.EXTRA_CASES[name]
+    nl = build().netlist()
+    a = [units.float(x) for x in an[1:]]
+    do, vo = backends.OracleSim(nl).tran(*a)
+    dr, vr = backends.RefSim(nl).tran(*a)
+    assert vo == vr
+    assert do.shape == dr.shape
+    frac, worst = parity.tight_fraction(do, dr)
+    assert frac >= MIN_TIGHT_FRACTION, (frac, worst)
+
+
 def test_oracle_step_statistics():
     """k = solves per accepted step, as probed on the reference."""
     _, _, sim, _, _ = _run_oracle("cfg4_ibis")
