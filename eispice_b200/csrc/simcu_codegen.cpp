@@ -192,6 +192,187 @@ void emitCalc(Out &o, const Program &p, int id, int dvar, const char *ind)
 			(dvar >= 0 && !st.back().d.empty()) ? st.back().d.c_str() : "0.0");
 }
 
+/* Value and ALL partial derivatives of calc `id` in one pass: the value chain
+ * is emitted once, each derivative chain only where it is structurally
+ * non-zero.  Per variable this is operation for operation what emitCalc()
+ * writes for that variable alone. */
+struct DualN { std::string f; std::vector<std::string> d; };
+
+void emitCalcGrad(Out &o, const Program &p, int id, const char *ind)
+{
+	const int c0 = p.calcOff[id], c1 = p.calcOff[id + 1];
+	const int v0 = p.calcVarOff[id], nv = p.calcVarOff[id + 1] - v0;
+	std::vector<char> want(nv, 0);
+	for (int v = 0; v < nv; v++) want[v] = (p.calcVars[v0 + v] != CALC_VAR_TIME);
+	std::vector<DualN> st;
+	int t = 0;
+	auto tmp = [&](const std::string &expr) {
+		char name[32];
+		std::snprintf(name, sizeof name, "t%d", t++);
+		o.f("%sconst double %s = %s;\n", ind, name, expr.c_str());
+		return std::string(name);
+	};
+	auto fresh = [&]() { DualN a; a.d.assign(nv, std::string()); return a; };
+	for (int pc = c0; pc < c1; pc += 2) {
+		const int op = p.calcCode[pc], arg = p.calcCode[pc + 1];
+		switch (op) {
+		case OP_CONST: { DualN a = fresh(); a.f = tmp(lit(p.calcConst[arg])); st.push_back(a); break; }
+		case OP_VAR: {
+			DualN a = fresh();
+			char nm[32];
+			std::snprintf(nm, sizeof nm, "v%d", arg);
+			a.f = nm;
+			if (want[arg]) a.d[arg] = tmp("1.0");
+			st.push_back(a);
+			break;
+		}
+		case OP_NEG: {
+			DualN &b = st.back();
+			b.f = tmp("-1 * " + b.f);
+			for (int v = 0; v < nv; v++) if (!b.d[v].empty()) b.d[v] = tmp("-1 * " + b.d[v]);
+			break;
+		}
+		case OP_ADD: case OP_SUB: {
+			const DualN c = st.back(); st.pop_back();
+			DualN &b = st.back();
+			const char *sgn = (op == OP_ADD) ? " + " : " - ";
+			b.f = tmp(b.f + sgn + c.f);
+			for (int v = 0; v < nv; v++) {
+				if (!b.d[v].empty() && !c.d[v].empty()) b.d[v] = tmp(b.d[v] + sgn + c.d[v]);
+				else if (!c.d[v].empty()) b.d[v] = (op == OP_ADD) ? c.d[v] : tmp("0.0 - " + c.d[v]);
+			}
+			break;
+		}
+		case OP_MUL: {
+			const DualN c = st.back(); st.pop_back();
+			DualN &b = st.back();
+			for (int v = 0; v < nv; v++) {
+				std::string d;
+				if (!b.d[v].empty() && !c.d[v].empty())
+					d = tmp(b.d[v] + " * " + c.f + " + " + b.f + " * " + c.d[v]);
+				else if (!b.d[v].empty()) d = tmp(b.d[v] + " * " + c.f);
+				else if (!c.d[v].empty()) d = tmp(b.f + " * " + c.d[v]);
+				b.d[v] = d;
+			}
+			b.f = tmp(b.f + " * " + c.f);
+			break;
+		}
+		case OP_DIV: {
+			const DualN c = st.back(); st.pop_back();
+			DualN &b = st.back();
+			std::string den;
+			for (int v = 0; v < nv; v++) {
+				std::string d;
+				if (!b.d[v].empty() || !c.d[v].empty()) {
+					std::string num;
+					if (!b.d[v].empty() && !c.d[v].empty())
+						num = b.d[v] + " * " + c.f + " - " + b.f + " * " + c.d[v];
+					else if (!b.d[v].empty()) num = b.d[v] + " * " + c.f;
+					else num = "0.0 - " + b.f + " * " + c.d[v];
+					if (den.empty()) den = tmp(c.f + " * " + c.f);
+					d = tmp("calcDiv((" + num + "), " + den + ", m)");
+				}
+				b.d[v] = d;
+			}
+			b.f = tmp("calcDiv(" + b.f + ", " + c.f + ", m)");
+			break;
+		}
+		case OP_POW: {
+			const DualN c = st.back(); st.pop_back();
+			DualN &b = st.back();
+			const std::string pw = tmp("pow(" + b.f + ", " + c.f + ")");
+			std::string ratio, lnb;
+			for (int v = 0; v < nv; v++) {
+				std::string d;
+				if (!b.d[v].empty() || !c.d[v].empty()) {
+					std::string left, right;
+					if (!b.d[v].empty()) {
+						if (ratio.empty()) ratio = tmp("calcDiv(" + c.f + ", " + b.f + ", m)");
+						left = b.d[v] + " * " + ratio;
+					}
+					if (!c.d[v].empty()) {
+						if (lnb.empty()) lnb = tmp("calcLn(" + b.f + ")");
+						right = "((" + b.f + " != 0.0) ? " + c.d[v] + " * " + lnb + " : 0.0)";
+					}
+					if (!left.empty() && !right.empty()) d = tmp(pw + " * (" + left + " + " + right + ")");
+					else d = tmp(pw + " * (" + (left.empty() ? right : left) + ")");
+				}
+				b.d[v] = d;
+			}
+			b.f = pw;
+			break;
+		}
+		case OP_FUNC: {
+			DualN &b = st.back();
+			/* the value and the derivative factor once, then one product per
+			 * variable: calcFunc(id, x, 1) returns f'(x) * 1 */
+			char fn[32], gn[32];
+			std::snprintf(fn, sizeof fn, "t%d", t++);
+			std::snprintf(gn, sizeof gn, "t%d", t++);
+			bool any = false;
+			for (int v = 0; v < nv; v++) any = any || !b.d[v].empty();
+			if (arg == FN_U) {
+				o.f("%sdouble %s, %s; calcFunc(%d, %s, 0.0, m, &%s, &%s);\n", ind, fn, gn, arg,
+						b.f.c_str(), fn, gn);
+				for (int v = 0; v < nv; v++) b.d[v] = want[v] ? std::string(gn) : std::string();
+			} else if (!any) {
+				o.f("%sdouble %s, %s; calcFunc(%d, %s, 0.0, m, &%s, &%s);\n", ind, fn, gn, arg,
+						b.f.c_str(), fn, gn);
+			} else {
+				/* keep the interpreter's rounding: it evaluates factor * x' with
+				 * the factor computed first, which is what factor * 1.0 * x' is
+				 * not in general - so emit one calcFunc per live variable and
+				 * let the compiler merge the shared transcendental calls */
+				bool first = true;
+				for (int v = 0; v < nv; v++) {
+					if (b.d[v].empty()) continue;
+					char fv[32], dv[32];
+					std::snprintf(fv, sizeof fv, "t%d", t++);
+					std::snprintf(dv, sizeof dv, "t%d", t++);
+					o.f("%sdouble %s, %s; calcFunc(%d, %s, %s, m, &%s, &%s);\n", ind, fv, dv, arg,
+							b.f.c_str(), b.d[v].c_str(), fv, dv);
+					if (first) { o.f("%sconst double %s = %s;\n", ind, fn, fv); first = false; }
+					b.d[v] = dv;
+				}
+			}
+			b.f = fn;
+			break;
+		}
+		case OP_GT: case OP_LT: case OP_GE: case OP_LE: case OP_EQ: case OP_NE: {
+			const DualN c = st.back(); st.pop_back();
+			DualN &b = st.back();
+			const char *rel = (op == OP_GT) ? ">" : (op == OP_LT) ? "<" : (op == OP_GE) ? ">="
+				: (op == OP_LE) ? "<=" : (op == OP_EQ) ? "==" : "!=";
+			b.f = tmp("(" + b.f + " " + rel + " " + c.f + ") ? 1.0 : 0.0");
+			b.d.assign(nv, std::string());
+			break;
+		}
+		case OP_NOT: {
+			DualN &b = st.back();
+			b.f = tmp("(" + b.f + " == 0.0) ? 1.0 : 0.0");
+			b.d.assign(nv, std::string());
+			break;
+		}
+		case OP_AND: case OP_OR: {
+			const DualN c = st.back(); st.pop_back();
+			DualN &b = st.back();
+			b.f = tmp("((" + b.f + " == 1.0) " + ((op == OP_AND) ? "&&" : "||") + " (" + c.f +
+					" == 1.0)) ? 1.0 : 0.0");
+			b.d.assign(nv, std::string());
+			break;
+		}
+		default: { /* OP_IF */
+			DualN &b = st.back();
+			b.f = tmp("(" + b.f + " != 0.0) ? 1.0 : 0.0");
+			b.d.assign(nv, std::string());
+			break;
+		}
+		}
+	}
+	for (int v = 0; v < nv; v++)
+		if (want[v]) o.f("%sg[%d] = %s;\n", ind, v, st.back().d[v].empty() ? "0.0" : st.back().d[v].c_str());
+}
+
 void emitCalcAll(Out &o, const Program &p)
 {
 	o.f("DEV void genCalc(Inst &c, int id, int dvar, double &f, double &dv)\n{\n");
@@ -214,6 +395,19 @@ void emitCalcAll(Out &o, const Program &p)
 			o.f("\t\t\tbreak;\n\t\t}\n");
 		}
 		o.f("\t\tdefault: break;\n\t\t}\n\t\tbreak;\n\t}\n");
+	}
+	o.f("\tdefault: break;\n\t}\n}\n\n");
+	o.f("DEV void genCalcGrad(Inst &c, int id, double *g)\n{\n");
+	o.f("\tconst double m = SIMCU_GMIN;\n\t(void)m; (void)c; (void)g;\n\tswitch (id) {\n");
+	for (int id = 0; id < ncalc; id++) {
+		const int v0 = p.calcVarOff[id], v1 = p.calcVarOff[id + 1];
+		o.f("\tcase %d: {\n", id);
+		for (int k = v0; k < v1; k++) {
+			if (p.calcVars[k] == CALC_VAR_TIME) o.f("\t\tconst double v%d = c.time;\n", k - v0);
+			else o.f("\t\tconst double v%d = c.X(%d);\n", k - v0, p.calcVars[k]);
+		}
+		emitCalcGrad(o, p, id, "\t\t");
+		o.f("\t\tbreak;\n\t}\n");
 	}
 	o.f("\tdefault: break;\n\t}\n}\n\n");
 }

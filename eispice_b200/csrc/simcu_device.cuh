@@ -617,6 +617,8 @@ DEV void wfNextStep(Inst &c, const int *d, int ib, double &next)
 /* generated per topology: value (dvar < 0) or one partial derivative of the
  * expression of calc id `id` at the current iterate */
 DEV void genCalc(Inst &c, int id, int dvar, double &f, double &dv);
+/* generated: all partial derivatives at once, g[calc variable] */
+DEV void genCalcGrad(Inst &c, int id, double *g);
 DEV void bSolve(Inst &c, const int *d, int dvar, double &f, double &dv)
 {
 	genCalc(c, d[DF_CALC], dvar, f, dv);
@@ -670,12 +672,21 @@ DEV void bLoad(Inst &c, const int *d, const int *bvIn)
 	const int nbv = d[DF_NBV];
 	const int *bv = bvOf(c, d, bvIn);
 	double eqCalc = c.S(sb);
+#ifdef SIMCU_JIT
+	double grad[CALC_MAX_VARS];
+	genCalcGrad(c, d[DF_CALC], grad);
+#endif
 	SIMCU_UNROLL
 	for (int k = 0; k < nbv && !c.err; k++) {
 		const int row = LDI(&bv[4 * k]), sA = LDI(&bv[4 * k + 1]);
 		const int sB = LDI(&bv[4 * k + 2]), cv = LDI(&bv[4 * k + 3]);
+#ifdef SIMCU_JIT
+		const double G = grad[cv];
+		if (isnan(G)) c.err = SIMCU_ERR_NAN;     /* calc.c:96 */
+#else
 		double f, G;
 		bSolve(c, d, cv, f, G);
+#endif
 		const double old = c.S(gb + k);
 		c.Aplus(sA, -(G - old));
 		if (type == DK_BI) c.Aplus(sB, (G - old));
