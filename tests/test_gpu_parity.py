@@ -336,3 +336,66 @@ def test_extra_circuits_match_the_oracle(name):
     frac, worst = parity.tight_fraction(data, od)
     assert frac >= MIN_TIGHT_FRACTION, (frac, worst)
     eng.close()
+
+
+def test_parameter_change_between_runs_equals_a_fresh_circuit():
+    """The reference's sweep mechanism: change a member (cct.R1.R = ...) and run
+    again - parameters are re-read through the borrowed pointers at every load
+    (SURVEY.md 3.1).  Same through this engine, with the compiled kernel reused."""
+    cct = circuits.cfg1_rc()
+    cct.tran('0.01n', '10n')
+    first = cct.results.copy()
+    cct.R1.R = 2.5e3
+    cct.tran('0.01n', '10n', restart=True)
+    second = cct.results.copy()
+    fresh = circuits.cfg1_rc()
+    fresh.R1.R = 2.5e3
+    fresh.tran('0.01n', '10n')
+    assert np.array_equal(second, fresh.results)
+    assert first.shape != second.shape or not np.array_equal(first, second)
+    assert cct._engine.stats()["jitCompiles"] <= 2      # the kernel is cached per topology + pivots
+    assert cct.check_v('out', float(np.interp(5e-9, fresh.t, fresh.results[:, fresh.variables.index('v(out)')])), '5n')
+
+
+def test_operating_point_of_a_chosen_instance():
+    """simcuRunOperatingPoint / simcuRunTransient address one instance of a batch."""
+    cct = circuits.vi_table()
+    M = 6
+    dc = np.array([10.0, -5.0, 0.0, 1.0, 5.0, 12.0])
+    want = np.array([10.0, -2.0, 1.0, 3.0, 8.0, 8.0])      # table of module/device.py:462-473
+    eng = engine.Engine(cct.netlist(), M)
+    eng.set_params({"Vx.DC": dc})
+    for i in range(M):
+        data, var = eng.op_single(instance=i)
+        assert data.shape == (1, len(var))
+        assert abs(data[0, var.index("i(VIx)")] - want[i]) < 1e-6 * max(1.0, abs(want[i]))
+        assert abs(data[0, var.index("v(1)")] - dc[i]) < 1e-12
+    eng.close()
+
+
+def test_full_size_properties_cfg4():
+    """BASELINE configs[3]: 256k IBIS corner/parameter sweep on one GPU.  Every
+    instance either finishes or is flagged (history ring), outputs stay inside
+    the supply rails (+ clamp overshoot), and a random subset re-run alone
+    reproduces the big batch bit for bit."""
+    w = workloads.make("cfg4", 262144)
+    probes = ["v(vo)"]
+    eng = engine.Engine(w.cct.netlist(), w.M)
+    res = eng.tran_batch(w.tstep, w.tstop, 0.0, w.params, probes)
+    ok = res.status == 0
+    assert ok.mean() > 0.999, "failed: %d" % (~ok).sum()
+    assert set(np.unique(res.status)) <= {0, 5}
+    v = res.data[ok, :, 0]
+    assert np.isfinite(v).all()
+    assert v.min() > -2.0 and v.max() < 7.0
+    st = res.stats
+    assert 2500 < st["accepted"] / w.M < 5000 and 3.5 < st["factorizations"] / st["accepted"] < 5.5
+    pick = np.random.default_rng(11).choice(np.nonzero(ok)[0], 64, replace=False)
+    small = engine.Engine(w.cct.netlist(), len(pick))
+    for ph in (0, 1):
+        small.set_pivots(ph, *eng.pivots(ph))
+    r2 = small.tran_batch(w.tstep, w.tstop, 0.0,
+                          {k: np.asarray(val)[pick] for k, val in w.params.items()}, probes)
+    assert np.array_equal(r2.data, res.data[pick])
+    small.close()
+    eng.close()
