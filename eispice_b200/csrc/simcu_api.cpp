@@ -106,6 +106,7 @@ struct _simcu {
 	int minBlocksUsed = 0, jitMinBlocks = -1;
 	double jitGmin = -1.0;
 	std::vector<char> active[2];
+	std::vector<double> consts[2];      /* per phase: literal value of a slot, NaN = varies */
 	std::shared_ptr<JitKernel> jit;
 	std::vector<int> jitProbes;
 	int jitTpb = 0, jitBlocks = 0, lanes = 32, lanesOpt = 0;
@@ -620,6 +621,12 @@ int analyseFrom(simcu_ *r, int ph, const DBuf &dA, int P)
 		for (int s = 0; s < p.nnzA; s++)
 			if (!active[s] && pilots[q][s] != 0.0) active[s] = 1;
 	r->active[ph] = active;
+	/* a slot the flattener believes is a literal must hold it in every pilot */
+	std::vector<double> cst = ph ? p.constTran : p.constOP;
+	for (size_t q = 0; q < pilots.size(); q++)
+		for (int s = 0; s < p.nnzA; s++)
+			if (cst[s] == cst[s] && pilots[q][s] != cst[s]) cst[s] = NAN;
+	r->consts[ph] = cst;
 	const bool forced = !r->forcePc[ph].empty();
 	if (forced && (int)r->forcePc[ph].size() != p.N) return fail("forced pivot sequence has the wrong length");
 	std::string err;
@@ -698,7 +705,7 @@ int buildJitKernel(simcu_ *r)
 	if (r->jit && r->jitProbes == r->probeRows && r->jitTpb == r->tpb &&
 			r->jitMinBlocks == r->minBlocksUsed && r->jitGmin == r->ctl.gmin)
 		return 0;
-	const std::string src = assembleSource(r->prog, r->sched, r->active, r->probeRows, r->tpb,
+	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows, r->tpb,
 			r->minBlocksUsed, r->ctl.gmin);
 	const std::string &key = src;
 	std::map<std::string, std::shared_ptr<JitKernel> >::iterator it = gKernelCache.find(key);
@@ -815,7 +822,7 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 	const bool needTran = !opOnly && (r->sched[1].lu.empty() || runChanged || !r->forcePc[1].empty());
 	if ((needOP || needTran) && pilotPass(r, needOP, needTran)) return -1;
 	if (opOnly && r->sched[1].lu.empty()) {
-		r->sched[1] = r->sched[0]; r->active[1] = r->active[0];
+		r->sched[1] = r->sched[0]; r->active[1] = r->active[0]; r->consts[1] = r->consts[0];
 		if (uploadSchedule(r, 1)) return -1;
 	}
 
@@ -1204,7 +1211,8 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 			return fail("%s", err.c_str());
 	}
 	const int tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
-	const std::string src = assembleSource(p, sched, active, probeRows, tpb, r->minBlocks, r->ctl.gmin);
+	const std::vector<double> consts[2] = {p.constOP, p.constTran};
+	const std::string src = assembleSource(p, sched, active, consts, probeRows, tpb, r->minBlocks, r->ctl.gmin);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;
 	std::string err;

@@ -480,7 +480,7 @@ void emitPhases(Out &o, const Program &p)
 
 /* ---- numeric LU + solves, straight-line --------------------------------------- */
 void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vector<char> &active,
-		int phase)
+		const std::vector<double> &cst, int phase)
 {
 	const int N = p.N, F = s.F;
 	o.f("/* %s: %d unknowns, %d matrix slots (%d fill), %d L + %d U off-diagonal entries */\n",
@@ -505,7 +505,12 @@ void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vec
 	}
 	for (int sl = 0; sl < F; sl++) {
 		if (!used[sl]) continue;
-		if (sl < p.nnzA && active[sl]) o.f("\tdouble w%d = c.Av[%d];\n", sl, sl);
+		/* +-1 incidence entries are literals: reciprocals of such pivots, and the
+		 * multipliers built from them, fold at compile time (1/1 and x*1 are
+		 * exact, so the results do not change), and the stamp needs no register */
+		if (sl < p.nnzA && active[sl] && cst[sl] == cst[sl])
+			o.f("\tdouble w%d = %s;\n", sl, lit(cst[sl]).c_str());
+		else if (sl < p.nnzA && active[sl]) o.f("\tdouble w%d = c.Av[%d];\n", sl, sl);
 		else o.f("\tdouble w%d = 0.0;\n", sl);
 	}
 	for (int r = 0; r < N; r++) o.f("\tdouble y%d = c.Bv[%d];\n", r, r);
@@ -570,14 +575,15 @@ std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock
 }
 
 std::string generateTopology(const Program &p, const Schedule sched[2],
-		const std::vector<char> active[2], const std::vector<int> &probeRows)
+		const std::vector<char> active[2], const std::vector<double> consts[2],
+		const std::vector<int> &probeRows)
 {
 	Out o;
 	o.f("/* ---- generated for this netlist by simcu_codegen.cpp ---- */\n");
 	emitCalcAll(o, p);
 	emitPhases(o, p);
-	emitFactorSolve(o, p, sched[0], active[0], 0);
-	emitFactorSolve(o, p, sched[1], active[1], 1);
+	emitFactorSolve(o, p, sched[0], active[0], consts[0], 0);
+	emitFactorSolve(o, p, sched[1], active[1], consts[1], 1);
 	emitRows(o, "genHistRows", p.histRows);
 	emitRows(o, "genProbeRows", probeRows);
 	return o.s;

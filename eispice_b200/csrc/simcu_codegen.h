@@ -17,10 +17,12 @@ std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock
 		double gmin);
 /* device records, expressions and the unrolled LU of both phases */
 std::string generateTopology(const Program &p, const Schedule sched[2],
-		const std::vector<char> active[2], const std::vector<int> &probeRows);
+		const std::vector<char> active[2], const std::vector<double> consts[2],
+		const std::vector<int> &probeRows);
 /* prelude + embedded library headers + topology + kernel */
 std::string assembleSource(const Program &p, const Schedule sched[2],
-		const std::vector<char> active[2], const std::vector<int> &probeRows,
+		const std::vector<char> active[2], const std::vector<double> consts[2],
+		const std::vector<int> &probeRows,
 		int threadsPerBlock, int minBlocks, double gmin);
 
 /* A compiled kernel.  compile() needs no GPU (NVRTC only); load() does. */

@@ -418,6 +418,16 @@ struct Flattener {
 	}
 	void mark(std::vector<char> &mask, int s) { if (s >= 0) mask[s] = 1; }
 	void both(int s) { mark(p.activeOP, s); mark(p.activeTran, s); }
+	/* every mention of a slot by a device; a slot keeps a constant only while
+	 * exactly one mention exists and that one sets a literal */
+	std::vector<int> refs;
+	void ref(int s) { if (s >= 0) refs[s]++; }
+	void lit(int s, double op, double tran)
+	{
+		if (s < 0) return;
+		refs[s]++;
+		p.constOP[s] = op; p.constTran[s] = tran;
+	}
 
 	/* one scalar parameter: per-instance row if the device has one */
 	int param(const Dev &d, const char *name, const double *src)
@@ -565,6 +575,8 @@ struct Flattener {
 		for (int c = 0; c < p.N; c++) p.colStart[c + 1] += p.colStart[c];
 		p.nnzA = (int)p.rowIdx.size();
 		p.activeOP.assign(p.nnzA, 0); p.activeTran.assign(p.nnzA, 0);
+		p.constOP.assign(p.nnzA, NAN); p.constTran.assign(p.nnzA, NAN);
+		refs.assign(p.nnzA, 0);
 		p.dev.assign((size_t)p.ndev * SIMCU_DEV_STRIDE, -1);
 		p.calcOff.assign(1, 0); p.calcVarOff.assign(1, 0);
 
@@ -595,25 +607,27 @@ struct Flattener {
 			switch (d.kind) {
 			case DK_R: {                       /* resistor.c:134-141 */
 				const int s[4] = {slot(K, K), slot(K, J), slot(J, K), slot(J, J)};
-				for (int j = 0; j < 4; j++) { rec[DF_A0 + j] = s[j]; both(s[j]); }
+				for (int j = 0; j < 4; j++) { rec[DF_A0 + j] = s[j]; both(s[j]); ref(s[j]); }
 				break;
 			}
 			case DK_C: {                       /* capacitor.c:250-257 */
 				const int s[4] = {slot(K, K), slot(K, J), slot(J, K), slot(J, J)};
-				for (int j = 0; j < 4; j++) { rec[DF_A0 + j] = s[j]; mark(p.activeTran, s[j]); }
+				for (int j = 0; j < 4; j++) { rec[DF_A0 + j] = s[j]; mark(p.activeTran, s[j]); ref(s[j]); }
 				sbase += 2 + INTEG_DOUBLES; ibase += 1;
 				break;
 			}
 			case DK_L: {                       /* inductor.c:251-266 */
 				const int s[5] = {slot(R, K), slot(R, J), slot(K, R), slot(J, R), slot(R, R)};
-				for (int j = 0; j < 4; j++) { rec[DF_A0 + j] = s[j]; both(s[j]); }
-				rec[DF_A0 + 4] = s[4]; mark(p.activeTran, s[4]);
+				static const double pm[4] = {1.0, -1.0, 1.0, -1.0};
+				for (int j = 0; j < 4; j++) { rec[DF_A0 + j] = s[j]; both(s[j]); lit(s[j], pm[j], pm[j]); }
+				rec[DF_A0 + 4] = s[4]; mark(p.activeTran, s[4]); ref(s[4]);
 				sbase += 2 + INTEG_DOUBLES; ibase += 1;
 				break;
 			}
 			case DK_V: {                       /* source_v.c:240-249 */
 				const int s[4] = {slot(R, K), slot(R, J), slot(K, R), slot(J, R)};
-				for (int j = 0; j < 4; j++) { rec[DF_SA0 + j] = s[j]; both(s[j]); }
+				static const double pm[4] = {1.0, -1.0, 1.0, -1.0};
+				for (int j = 0; j < 4; j++) { rec[DF_SA0 + j] = s[j]; both(s[j]); lit(s[j], pm[j], pm[j]); }
 				sbase += 2 + CB_DOUBLES; ibase += 2;
 				break;
 			}
@@ -627,10 +641,14 @@ struct Flattener {
 					slot(S, L), slot(S, Mm), slot(L, S), slot(Mm, S), slot(S, K), slot(S, J),
 					slot(R, R), slot(S, S), slot(K, S), slot(J, S), slot(L, R), slot(Mm, R)};
 				static const char inTran[18] = {1, 1, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 1, 1, 0, 0, 0, 0};
+				/* devLoad (tline.c:236-267) and devInitStep (:104-111) literals */
+				static const double atOP[18] = {1, -1, 1, -1, -1, 1, 1, -1, 1, -1, -1, 1, 0, 0, 1, -1, -1, 1};
 				for (int j = 0; j < 18; j++) {
 					rec[DF_TA0 + j] = s[j];
 					mark(p.activeOP, s[j]);
 					if (inTran[j]) mark(p.activeTran, s[j]);
+					if (j == 12 || j == 13) ref(s[j]);          /* RR, SS = -Z0 */
+					else lit(s[j], atOP[j], inTran[j] ? atOP[j] : 0.0);
 				}
 				const int rows[6] = {R, S, K, J, L, Mm};
 				for (int j = 0; j < 6; j++) rec[DF_TH0 + j] = rows[j] ? histCol[rows[j]] : -1;
@@ -640,7 +658,11 @@ struct Flattener {
 			case DK_VI: {                      /* vicurve.c:333-356 */
 				const int s[8] = {slot(R, K), slot(R, S), slot(K, R), slot(S, R),
 					slot(J, J), slot(J, S), slot(S, J), slot(S, S)};
-				for (int j = 0; j < 8; j++) { rec[DF_VA0 + j] = s[j]; both(s[j]); }
+				static const double pm[4] = {1.0, -1.0, 1.0, -1.0};
+				for (int j = 0; j < 8; j++) {
+					rec[DF_VA0 + j] = s[j]; both(s[j]);
+					if (j < 4) lit(s[j], pm[j], pm[j]); else ref(s[j]);
+				}
 				sbase += 4 + CB_DOUBLES; ibase += 4;
 				break;
 			}
@@ -665,23 +687,25 @@ struct Flattener {
 					int sA, sB = -1;
 					if (d.kind == DK_BI) { sA = slot(J, x); sB = slot(S, x); }   /* nonlinear_i.c:163-188 */
 					else sA = slot(R, x);                                        /* _v.c:134-156, _c.c:142-164 */
-					both(sA); both(sB);
+					both(sA); both(sB); ref(sA); ref(sB);
 					p.bvar.push_back(x); p.bvar.push_back(sA); p.bvar.push_back(sB);
 					p.bvar.push_back(d.bvCalcVar[i]);
 				}
 				if (d.kind == DK_BI) {         /* nonlinear_i.c:402-417: RK RM KR MR */
 					const int s[4] = {slot(R, K), slot(R, S), slot(K, R), slot(S, R)};
-					for (int j = 0; j < 4; j++) { rec[DF_BA0 + j] = s[j]; both(s[j]); }
+					static const double pm[4] = {1.0, -1.0, 1.0, -1.0};
+					for (int j = 0; j < 4; j++) { rec[DF_BA0 + j] = s[j]; both(s[j]); lit(s[j], pm[j], pm[j]); }
 					sbase += 4 + CB_DOUBLES + (int)d.bvRow.size(); ibase += 2;
 				} else if (d.kind == DK_BV) {  /* nonlinear_v.c:371-384: RK RJ KR JR */
 					const int s[4] = {slot(R, K), slot(R, J), slot(K, R), slot(J, R)};
-					for (int j = 0; j < 4; j++) { rec[DF_BA0 + j] = s[j]; both(s[j]); }
+					static const double pm[4] = {1.0, -1.0, 1.0, -1.0};
+					for (int j = 0; j < 4; j++) { rec[DF_BA0 + j] = s[j]; both(s[j]); lit(s[j], pm[j], pm[j]); }
 					sbase += 4 + CB_DOUBLES + (int)d.bvRow.size(); ibase += 2;
 				} else {                       /* nonlinear_c.c:465-485: KK KJ JK JJ RC CR */
 					const int s[6] = {slot(K, K), slot(K, J), slot(J, K), slot(J, J),
 						slot(R, S), slot(S, R)};
-					for (int j = 0; j < 4; j++) { rec[DF_BA0 + j] = s[j]; mark(p.activeTran, s[j]); }
-					for (int j = 4; j < 6; j++) { rec[DF_BA0 + j] = s[j]; both(s[j]); }
+					for (int j = 0; j < 4; j++) { rec[DF_BA0 + j] = s[j]; mark(p.activeTran, s[j]); ref(s[j]); }
+					for (int j = 4; j < 6; j++) { rec[DF_BA0 + j] = s[j]; both(s[j]); lit(s[j], 1.0, 1.0); }
 					sbase += 2 + INTEG_DOUBLES + 4 + (int)d.bvRow.size(); ibase += 2;
 				}
 				break;
@@ -690,6 +714,8 @@ struct Flattener {
 			}
 		}
 		p.stateDoubles = sbase; p.stateInts = ibase;
+		for (int sl = 0; sl < p.nnzA; sl++)
+			if (refs[sl] != 1) { p.constOP[sl] = NAN; p.constTran[sl] = NAN; }
 		return parameters(true);
 	}
 };

@@ -84,6 +84,9 @@ struct Program {
 	int ninst = 0, niinst = 0;
 	int stateDoubles = 0, stateInts = 0;
 	std::vector<char> activeOP, activeTran;       /* [nnzA] slot can be non-zero */
+	/* slots that hold the same compile-time constant for every instance in a
+	 * phase (+-1 incidence entries of branch rows): [nnzA], NaN = not constant */
+	std::vector<double> constOP, constTran;
 	int maxCalcStack = 0;
 };
 

@@ -77,14 +77,15 @@ const char *jitNvrtcPath() { return gNvrtc.path.c_str(); }
 void jitSetNvrtcPath(const char *path) { gNvrtcHint = path ? path : ""; }
 
 std::string assembleSource(const Program &p, const Schedule sched[2],
-		const std::vector<char> active[2], const std::vector<int> &probeRows,
+		const std::vector<char> active[2], const std::vector<double> consts[2],
+		const std::vector<int> &probeRows,
 		int threadsPerBlock, int minBlocks, double gmin)
 {
 	std::string s = generatePrelude(p, (int)probeRows.size(), threadsPerBlock, minBlocks, gmin);
 	s += kSrcProgram;
 	s += kSrcCalc;
 	s += kSrcDevice;
-	s += generateTopology(p, sched, active, probeRows);
+	s += generateTopology(p, sched, active, consts, probeRows);
 	s += kSrcJitKernel;
 	return s;
 }
