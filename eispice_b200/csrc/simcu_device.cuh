@@ -884,12 +884,13 @@ DEV void devInitStep(Inst &c, const int *d)
 /* T-line delayed lookup: history_interp.c:42-92, history.c:36-59.  Records
  * are kept in a ring of a.histRecords entries; `count` records exist so far,
  * record r lives in slot r % R.  Returns false if the needed record is gone. */
+DEV int tlineWrap(int p, int R) { return (p >= R) ? p - R : ((p < 0) ? p + R : p); }
+
 /* Finds the two history records that bracket (or, past the newest record,
  * precede) the delayed time tp.  ring = this thread's records, `rec` doubles
  * each, column 0 = time; record q lives at position q % R.  Returns (hint,
  * position of the earlier record, position of the later one, position of the
- * hint record + 1 or 0 = the needed record is gone).
- * One modulo per call; positions wrap by comparison while walking. */
+ * hint record + 1 or 0 = the needed record is gone).  One modulo per call. */
 DEVFN int4 tlineLocateFn(const double *ring, int R, int rec, int count, int hint, double tp)
 {
 	int4 r;
@@ -897,21 +898,39 @@ DEVFN int4 tlineLocateFn(const double *ring, int R, int rec, int count, int hint
 	const int lo = (count > R) ? count - R : 0;
 	int i = hint;
 	if (i < lo || i >= count) i = lo;
-	int pos = i % R;
-	double ti = ring[(size_t)pos * rec];
-	while (ti > tp && i > lo) {
-		i--; pos = (pos == 0) ? R - 1 : pos - 1;
-		ti = ring[(size_t)pos * rec];
+	const int i0 = i, base = i % R;
+	/* time of record j in [lo, count): |j - i0| < R, so one wrap at most */
+	#define HTIME(j) ring[(size_t)tlineWrap(base + ((j) - i0), R) * rec]
+	/* The reference walks record by record from the hint (history_interp.c:
+	 * 42-92).  Accepted times increase strictly, so the record it lands on is
+	 * THE largest j with t_j <= tp; a galloping + binary search finds the same j
+	 * in O(log distance) dependent loads - the walk is long whenever one big
+	 * step follows a burst of tiny ones, and a warp waits for its slowest lane. */
+	int a, b;                                 /* t_a <= tp, and b == count or t_b > tp */
+	if (HTIME(i) > tp) {
+		if (i == lo) return r;                /* fell off the ring */
+		b = i;
+		int step = 1, j = i - 1;
+		while (j > lo && HTIME(j) > tp) { b = j; j = (j - step > lo) ? j - step : lo; step <<= 1; }
+		if (HTIME(j) > tp) return r;
+		a = j;
+	} else {
+		a = i; b = count;
+		int step = 1, j = i + 1, probes = 0;
+		while (j < count) {
+			if (HTIME(j) <= tp) { a = j; if (++probes > 1) step <<= 1; j = a + step; }
+			else { b = j; break; }
+		}
 	}
-	if (ti > tp) return r;                    /* fell off the ring */
-	int pn = (pos + 1 == R) ? 0 : pos + 1;
-	while (i + 1 < count) {
-		const double tn = ring[(size_t)pn * rec];
-		if (!(tn <= tp)) break;
-		i++; pos = pn; pn = (pos + 1 == R) ? 0 : pos + 1;
+	while (b - a > 1) {
+		const int mid = a + ((b - a) >> 1);
+		if (HTIME(mid) <= tp) a = mid; else b = mid;
 	}
+	#undef HTIME
+	i = a;
+	const int pos = tlineWrap(base + (i - i0), R);
 	r.x = i;
-	if (i + 1 < count) { r.y = pos; r.z = pn; }
+	if (i + 1 < count) { r.y = pos; r.z = (pos + 1 == R) ? 0 : pos + 1; }
 	else {                                    /* extrapolate from the last two */
 		if (i - 1 < lo) return r;
 		r.y = (pos == 0) ? R - 1 : pos - 1; r.z = pos;
