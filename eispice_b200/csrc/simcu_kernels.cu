@@ -1,22 +1,18 @@
 /*
- * simcu_kernels.cu - device side of the batched transient engine (sm_100a).
+ * simcu_kernels.cu - the GENERIC kernels of the batched transient engine
+ * (sm_100a): table-driven versions of load, operating point and transient that
+ * walk the device records, the LU op-stream and the expression bytecode from
+ * global memory.  They run the pilot pass (the matrices that decide the pivot
+ * sequences must exist before a topology-specialised kernel can be generated,
+ * simcu_api.cpp: pilotPass) and serve as an independent implementation in the
+ * tests (option interpreter = 1).  Production batches run simcu_jit_kernel.cuh.
  *
- * One thread owns one instance for the whole run.  All per-instance data is
- * structure-of-arrays with the instance index fastest (simcu_program.h), so
- * every stamp, state access, LU load and solution store of a warp is one
- * coalesced 256-byte line.  The numeric LU works on a per-thread workspace of
- * F + N doubles that sits in SHARED memory ([slot][blockDim], conflict-free)
- * whenever it fits, so a Newton iteration costs HBM only nnzA + N loads; the
- * factors never leave the SM.  The elimination order, fill pattern and pivot
- * sequence are fixed on the host (simcu_host.cpp: symbolic analysis on a pilot
- * batch) and arrive as an op-stream that every thread of a warp walks in
- * lock-step - warp-uniform control flow, data-dependent divergence only in
- * the Newton / step-rejection loop trip counts.
- *
- * Semantics follow the reference file:line cited at each function (paths
- * relative to the reference root); tests/ compare every phase with the CPU
- * oracle.  FP64 CUDA cores only: the work is sparse, N <= ~100 and
- * memory-bound, there is nothing to give the tensor cores.
+ * One thread owns one instance.  All per-instance data is structure-of-arrays
+ * with the instance index fastest (simcu_program.h), so every stamp, state
+ * access, LU load and solution store of a warp is one coalesced line.  The
+ * numeric LU works on a per-thread workspace of F + N doubles in shared memory
+ * ([slot][blockDim], conflict-free) whenever it fits.  The device functions
+ * themselves are shared with the specialised kernel: simcu_device.cuh.
  */
 #include <cuda_runtime.h>
 #include <math.h>

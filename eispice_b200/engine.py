@@ -397,11 +397,13 @@ class Engine:
     def compile_only(self, probes=()):
         """(source text, cubin bytes) of the topology-specialised kernel; needs
         NVRTC but no GPU."""
-        src = C.c_char_p()
+        src = C.c_void_p()
         n = C.c_int()
         rc = self.L.simcuCompileOnly(self.h, self._probe_array(probes), len(probes),
                                      C.byref(src), C.byref(n))
-        text = src.value.decode() if src.value else ""
+        text = C.string_at(src).decode() if src.value else ""
+        if src.value:
+            self.L.simcuFree(src)
         if rc != 0:
             raise RuntimeError("simcuCompileOnly failed")
         return text, n.value
