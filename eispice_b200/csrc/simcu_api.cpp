@@ -101,6 +101,7 @@ struct _simcu {
 	std::vector<int> probeRows;
 	int ngrid = 0, histRecords = 0, tpb = 64, wsShared = 1;
 	int interpreter = 0;            /* 1: run the batch on the generic kernels */
+	int keepOrder = 0;              /* 1: do not group instances by table set */
 	int minBlocks = 0;              /* __launch_bounds__ second argument */
 	int maxBlocksPerSM = 0;         /* cap on resident blocks (0 = occupancy limit) */
 	int minBlocksUsed = 0, jitMinBlocks = -1;
@@ -115,7 +116,7 @@ struct _simcu {
 	/* device memory */
 	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
 		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
-		dProbeRows, dPmap, dPconst, dPinst, dIinst;
+		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder;
 	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dOutRaw, dWs, dRemaining;
 	int *hRemaining = nullptr;      /* pinned */
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -134,7 +135,7 @@ struct _simcu {
 	~_simcu()
 	{
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
-			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP,
+			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder,
 			&dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
 			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dOutRaw,
 			&dWs, &dRemaining};
@@ -500,6 +501,7 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "num_pilots") r->numPilots = std::max(1, (int)value);
 	else if (n == "interpreter") r->interpreter = (value != 0.0);
 	else if (n == "lanes_per_warp") r->lanesOpt = (int)value;
+	else if (n == "keep_order") r->keepOrder = (value != 0.0);
 	else if (n == "min_blocks_per_sm") { r->minBlocks = (int)value; r->jit.reset(); }
 	else if (n == "max_blocks_per_sm") r->maxBlocksPerSM = (int)value;
 	else return fail("unknown option %s", name);
@@ -548,8 +550,25 @@ int uploadParameters(simcu_ *r, cudaStream_t st)
 			r->dTabOff.upload(p.tabOff, st) || r->dTabType.upload(p.tabType, st) ||
 			r->dTabP.upload(p.tabP, st))
 		return -1;
+	/* processing order: stable sort by the tuple of table-set indices */
+	const int *order = nullptr;
+	if (p.niinst > 0 && !r->keepOrder) {
+		const int M = r->M;
+		std::vector<int> ord(M);
+		for (int i = 0; i < M; i++) ord[i] = i;
+		std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
+			for (int k = 0; k < p.niinst; k++) {
+				const int vx = p.iinst[(size_t)k * M + x], vy = p.iinst[(size_t)k * M + y];
+				if (vx != vy) return vx < vy;
+			}
+			return false;
+		});
+		if (r->dOrder.upload(ord, st)) return -1;
+		order = r->dOrder.as<int>();
+	}
 	for (int ph = 0; ph < 2; ph++) {
 		SimcuArgs &a = r->args[ph];
+		a.order = order;
 		a.pmap = r->dPmap.as<int>(); a.pconst = r->dPconst.as<double>();
 		a.pinst = r->dPinst.as<double>(); a.iinst = r->dIinst.as<int>();
 		a.tabOff = r->dTabOff.as<int>(); a.tabType = r->dTabType.as<int>();

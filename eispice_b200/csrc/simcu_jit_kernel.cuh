@@ -166,7 +166,12 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 		if (lane == 0) base = atomicAdd(a.counter, a.lanes);
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= a.M) break;
-		if (lane < a.lanes && base + lane < a.M) jitRunInstance(a, base + lane, slot, hstride, opOnly);
+		if (lane < a.lanes && base + lane < a.M) {
+			/* instances are processed grouped by table set (IBIS corner), so the
+			 * lanes of a warp follow similar waveforms and diverge less */
+			const int inst = a.order ? __ldg(&a.order[base + lane]) : base + lane;
+			jitRunInstance(a, inst, slot, hstride, opOnly);
+		}
 		__syncwarp();
 	}
 }

@@ -145,6 +145,7 @@ typedef struct {
 	int stopBeforeSolve;      /* pilot: assemble the first attempt, then stop */
 	int *counter;             /* specialised kernel: next unclaimed instance */
 	int lanes;                /* active lanes per warp (power of two <= 32) */
+	const int *order;         /* processing order of the instances (NULL = as given) */
 } SimcuArgs;
 
 #endif

@@ -130,7 +130,8 @@ int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
  * minstep (control.h:34-56); hist_records, max_attempts, attempts_per_launch,
  * threads_per_block, workspace_shared (0/1), raw_max_points, raw_first,
  * raw_count, pivot_threshold, num_pilots, min_blocks_per_sm (of the specialised
- * kernel: bounds its registers, 0 = compiler's choice), lanes_per_warp (0 = automatic), interpreter (1: run the batch on the generic
+ * kernel: bounds its registers, 0 = compiler's choice), lanes_per_warp (0 = automatic), keep_order (1: do not group instances by
+ * table set for processing), interpreter (1: run the batch on the generic
  * table-driven kernels instead of the NVRTC-specialised one; for verification);
  * r = NULL: quiet (0/1) */
 int simcuSetOption(simcu_ *r, char *name, double value);
