@@ -102,6 +102,7 @@ struct _simcu {
 	int ngrid = 0, histRecords = 0, tpb = 64, wsShared = 1;
 	int interpreter = 0;            /* 1: run the batch on the generic kernels */
 	int keepOrder = 0;              /* 1: do not group instances by table set */
+	int historyRetry = 0;           /* 1: re-run instances that outran the history ring */
 	int minBlocks = 0;              /* __launch_bounds__ second argument */
 	int maxBlocksPerSM = 0;         /* cap on resident blocks (0 = occupancy limit) */
 	int minBlocksUsed = 0, jitMinBlocks = -1;
@@ -116,7 +117,7 @@ struct _simcu {
 	/* device memory */
 	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
 		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
-		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder;
+		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2;
 	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dOutRaw, dWs, dRemaining;
 	int *hRemaining = nullptr;      /* pinned */
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -135,7 +136,7 @@ struct _simcu {
 	~_simcu()
 	{
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
-			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder,
+			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder, &dOrder2,
 			&dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
 			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dOutRaw,
 			&dWs, &dRemaining};
@@ -502,6 +503,7 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "interpreter") r->interpreter = (value != 0.0);
 	else if (n == "lanes_per_warp") r->lanesOpt = (int)value;
 	else if (n == "keep_order") r->keepOrder = (value != 0.0);
+	else if (n == "history_retry") r->historyRetry = (value != 0.0);
 	else if (n == "min_blocks_per_sm") { r->minBlocks = (int)value; r->jit.reset(); }
 	else if (n == "max_blocks_per_sm") r->maxBlocksPerSM = (int)value;
 	else return fail("unknown option %s", name);
@@ -685,7 +687,7 @@ int pilotPass(simcu_ *r, bool needOP, bool needTran)
 				cudaMemset(b.IS.p, 0, std::max(1, p.stateInts) * m4) != cudaSuccess)
 			break;
 		SimcuArgs a = r->args[0];
-		a.M = P; a.pinst = b.pinst.as<double>(); a.iinst = b.iinst.as<int>();
+		a.M = P; a.count = P; a.order = nullptr; a.pinst = b.pinst.as<double>(); a.iinst = b.iinst.as<int>();
 		a.A = b.A.as<double>(); a.B = b.B.as<double>(); a.X = b.X.as<double>();
 		a.S = b.S.as<double>(); a.IS = b.IS.as<int>(); a.CD = b.CD.as<double>();
 		a.CI = b.CI.as<int>(); a.Ht = b.Ht.as<double>(); a.Hx = b.Hx.as<double>();
@@ -934,11 +936,55 @@ int runDevice(simcu_ *r, cudaStream_t st, bool opOnly)
 		CU(cudaMemsetAsync(r->dRemaining.p, 0, 2 * sizeof(int), st));
 		CU(cudaEventRecord(r->ev2, st));
 		int op = opOnly ? 1 : 0;
+		r->args[1].count = r->M;
 		void *params[] = {(void *)&r->args[1], (void *)&op};
 		cudaError_t e = cudaLaunchKernel((const void *)r->jit->kernel, dim3(r->jitBlocks), dim3(r->tpb),
 				params, 0, st);
 		if (e != cudaSuccess) return fail("specialised kernel launch failed: %s", cudaGetErrorString(e));
 		launches = 1;
+		r->stats.historyRetries = 0;
+		if (!opOnly && r->histRecords > 0 && r->historyRetry) {
+			/* Instances that outran the T-line history ring (a burst of tiny steps
+			 * longer than the ring inside one line delay) run again on their own:
+			 * the same ring memory shared by few threads is orders of magnitude
+			 * deeper.  The reference keeps the whole history and never fails here. */
+			std::vector<int> status(r->M), acc(r->M), rejl(r->M), rejn(r->M);
+			const int *ci = r->dCI.as<int>();
+			const size_t mb = (size_t)r->M * 4;
+			CU(cudaMemcpyAsync(status.data(), ci + (size_t)CI_STATUS * r->M, mb, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(acc.data(), ci + (size_t)CI_ACCEPTED * r->M, mb, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(rejl.data(), ci + (size_t)CI_REJ_LTE * r->M, mb, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(rejn.data(), ci + (size_t)CI_REJ_NC * r->M, mb, cudaMemcpyDeviceToHost, st));
+			CU(cudaStreamSynchronize(st));
+			std::vector<int> again;
+			long long okAttempts = 0, okCount = 0;
+			for (int i = 0; i < r->M; i++) {
+				if (status[i] == SIMCU_ERR_HISTORY) again.push_back(i);
+				else if (status[i] == 0) { okAttempts += (long long)acc[i] + rejl[i] + rejn[i]; okCount++; }
+			}
+			const int n2 = (int)again.size();
+			const long long slots1 = (long long)r->jitBlocks * (r->tpb / 32) * r->lanes;
+			if (n2 > 0 && n2 * 4LL <= slots1) {
+				const int blocks2 = (n2 + r->tpb - 1) / r->tpb;
+				const long long slots2 = (long long)blocks2 * (r->tpb / 32) * r->lanes;
+				const long long deeper = (long long)r->histRecords * slots1 / slots2;
+				SimcuArgs a2 = r->args[1];
+				a2.histRecords = (int)std::min<long long>(deeper, 1LL << 30);
+				a2.count = n2;
+				/* instances whose step size has collapsed would run for minutes:
+				 * give the second pass 32 x the attempts of an average instance */
+				if (okCount > 0)
+					a2.maxAttempts = std::min(a2.maxAttempts, 32 * (okAttempts / okCount) + 1000);
+				if (r->dOrder2.upload(again, st)) return -1;
+				a2.order = r->dOrder2.as<int>();
+				CU(cudaMemsetAsync(r->dRemaining.p, 0, 2 * sizeof(int), st));
+				void *params2[] = {(void *)&a2, (void *)&op};
+				e = cudaLaunchKernel((const void *)r->jit->kernel, dim3(blocks2), dim3(r->tpb), params2, 0, st);
+				if (e != cudaSuccess) return fail("retry launch failed: %s", cudaGetErrorString(e));
+				launches++;
+				r->stats.historyRetries = n2;
+			}
+		}
 	}
 	CU(cudaEventRecord(r->ev1, st));
 	CU(cudaStreamSynchronize(st));

@@ -165,8 +165,8 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 		int base = 0;
 		if (lane == 0) base = atomicAdd(a.counter, a.lanes);
 		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= a.M) break;
-		if (lane < a.lanes && base + lane < a.M) {
+		if (base >= a.count) break;
+		if (lane < a.lanes && base + lane < a.count) {
 			/* instances are processed grouped by table set (IBIS corner), so the
 			 * lanes of a warp follow similar waveforms and diverge less */
 			const int inst = a.order ? __ldg(&a.order[base + lane]) : base + lane;

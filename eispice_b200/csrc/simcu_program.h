@@ -146,6 +146,7 @@ typedef struct {
 	int *counter;             /* specialised kernel: next unclaimed instance */
 	int lanes;                /* active lanes per warp (power of two <= 32) */
 	const int *order;         /* processing order of the instances (NULL = as given) */
+	int count;                /* instances this launch processes (<= M; M stays the stride) */
 } SimcuArgs;
 
 #endif

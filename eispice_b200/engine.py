@@ -40,7 +40,8 @@ class Stats(C.Structure):
                 ("deviceMs", C.c_double), ("tranMs", C.c_double),
                 ("jitCompiles", C.c_int), ("registersPerThread", C.c_int),
                 ("localBytesPerThread", C.c_int), ("gridBlocks", C.c_int),
-                ("lanesPerWarp", C.c_int), ("pivotBreakdowns", C.c_longlong)]
+                ("lanesPerWarp", C.c_int), ("pivotBreakdowns", C.c_longlong),
+                ("historyRetries", C.c_int)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

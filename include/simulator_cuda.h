@@ -68,6 +68,7 @@ typedef struct {
 	int gridBlocks;
 	int lanesPerWarp;          /* instances per warp of the specialised kernel */
 	long long pivotBreakdowns; /* transient attempts rejected for a zero pivot */
+	int historyRetries;        /* instances re-run with a deeper T-line history ring */
 } simcuStats_;
 
 /* simulatorNew (simulator.h:33): r must be NULL */
@@ -131,7 +132,9 @@ int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
  * threads_per_block, workspace_shared (0/1), raw_max_points, raw_first,
  * raw_count, pivot_threshold, num_pilots, min_blocks_per_sm (of the specialised
  * kernel: bounds its registers, 0 = compiler's choice), lanes_per_warp (0 = automatic), keep_order (1: do not group instances by
- * table set for processing), interpreter (1: run the batch on the generic
+ * table set for processing), history_retry (1: re-run instances that
+ * outran the T-line history ring, with a deeper ring and 32 x the attempts of
+ * an average instance), interpreter (1: run the batch on the generic
  * table-driven kernels instead of the NVRTC-specialised one; for verification);
  * r = NULL: quiet (0/1) */
 int simcuSetOption(simcu_ *r, char *name, double value);

@@ -399,3 +399,37 @@ def test_full_size_properties_cfg4():
     assert np.array_equal(r2.data, res.data[pick])
     small.close()
     eng.close()
+
+
+def test_history_ring_overflow_is_retried_with_a_deeper_ring():
+    """An instance whose T-line delay spans more accepted steps than the history
+    ring holds is flagged by the first pass and re-run on its own with the ring
+    memory of the whole batch (the reference keeps the complete history)."""
+    cct = circuits.tline()
+    M = 256
+    td = np.full(M, 0.2e-9)
+    slow = [5, 100, 201]
+    td[slow] = 2.5e-9
+    probes = ["v(vo)", "i(Vx)"]
+
+    eng = engine.Engine(cct.netlist(), M)
+    res = eng.tran_batch(0.01e-9, 10e-9, 0.0, {"Tg.Td": td}, probes, hist_records=200,
+                         history_retry=0)
+    assert sorted(np.nonzero(res.status == 5)[0]) == slow and res.stats["historyRetries"] == 0
+    eng.close()
+
+    eng = engine.Engine(cct.netlist(), M)
+    res = eng.tran_batch(0.01e-9, 10e-9, 0.0, {"Tg.Td": td}, probes, hist_records=200,
+                         history_retry=1)
+    assert (res.status == 0).all()
+    assert res.stats["historyRetries"] == len(slow) and res.stats["kernelLaunches"] == 2
+    for i in slow + [0]:
+        nl = [tuple(list(d[:7]) + [float(td[i])] + list(d[8:])) if d[0] == "T" else d
+              for d in cct.netlist()]
+        od, ov = backends.OracleSim(nl).tran(0.01e-9, 10e-9)
+        od = parity.drop_degenerate(od, 0.01e-9)
+        for p, name in enumerate(probes):
+            ref = np.interp(res.grid, od[:, 0], od[:, ov.index(name)])
+            tol = parity.RELTOL * np.abs(ref).max() + (parity.VNTOL if name[0] == "v" else parity.ABSTOL)
+            assert np.abs(res.data[i, :, p] - ref).max() < tol, (i, name)
+    eng.close()
