@@ -109,6 +109,7 @@ struct _simcu {
 	double jitGmin = -1.0;
 	std::vector<char> active[2];
 	std::vector<double> consts[2];      /* per phase: literal value of a slot, NaN = varies */
+	std::vector<int> orderKey;          /* table-set indices the processing order was built from */
 	std::shared_ptr<JitKernel> jit;
 	std::vector<int> jitProbes;
 	int jitTpb = 0, jitBlocks = 0, lanes = 32, lanesOpt = 0;
@@ -554,8 +555,11 @@ int uploadParameters(simcu_ *r, cudaStream_t st)
 		return -1;
 	/* processing order: stable sort by the tuple of table-set indices */
 	const int *order = nullptr;
-	if (p.niinst > 0 && !r->keepOrder) {
+	if (p.niinst > 0 && !r->keepOrder && r->orderKey == p.iinst && r->dOrder.p) {
+		order = r->dOrder.as<int>();          /* table sets unchanged since the last upload */
+	} else if (p.niinst > 0 && !r->keepOrder) {
 		const int M = r->M;
+		r->orderKey = p.iinst;
 		std::vector<int> ord(M);
 		for (int i = 0; i < M; i++) ord[i] = i;
 		std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
