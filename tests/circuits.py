@@ -348,6 +348,17 @@ def ibis_fixture():
                                for sp in ("typ", "min", "max")}
                           for dr in ("rising", "falling")}
             models[name] = m
+        # V-t waveforms, fixtures and ramp data (tests/golden/make_ibis_vt.py)
+        vt = np.load(_os.path.join(_os.path.dirname(path), "ibis_vt.npz"))
+        vmeta = _json.loads(str(vt["meta"]))
+        for name, vm in vmeta.items():
+            for direction, waves in vm["waveforms"].items():
+                models[name][direction + "_waveform"] = [
+                    dict(w, data={sp: vt["%s/%s/%d/%s" % (name, direction, k, sp)]
+                                  for sp in ("typ", "min", "max")})
+                    for k, w in enumerate(waves)]
+            if vm["ramp"]:
+                models[name]["ramp"] = vm["ramp"]
         _IBIS = (models, meta["pins"])
     return _IBIS
 
