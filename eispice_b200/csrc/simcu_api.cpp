@@ -110,6 +110,9 @@ struct _simcu {
 	std::vector<char> active[2];
 	std::vector<double> consts[2];      /* per phase: literal value of a slot, NaN = varies */
 	std::vector<int> orderKey;          /* table-set indices the processing order was built from */
+	std::vector<int> measures;          /* (kind, row) pairs */
+	std::vector<double> measureLevels;
+	std::vector<int> jitMeasures;
 	std::shared_ptr<JitKernel> jit;
 	std::vector<int> jitProbes;
 	int jitTpb = 0, jitBlocks = 0, lanes = 32, lanesOpt = 0;
@@ -118,7 +121,7 @@ struct _simcu {
 	/* device memory */
 	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
 		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
-		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2;
+		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2, dMeasure, dMeasureLevel;
 	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dOutRaw, dWs, dRemaining;
 	int *hRemaining = nullptr;      /* pinned */
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -137,8 +140,8 @@ struct _simcu {
 	~_simcu()
 	{
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
-			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder, &dOrder2,
-			&dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
+			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder, &dOrder2, &dMeasure,
+			&dMeasureLevel, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
 			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dOutRaw,
 			&dWs, &dRemaining};
 		for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) all[i]->release();
@@ -728,10 +731,11 @@ std::map<std::string, std::shared_ptr<JitKernel> > gKernelCache;
 int buildJitKernel(simcu_ *r)
 {
 	if (r->jit && r->jitProbes == r->probeRows && r->jitTpb == r->tpb &&
-			r->jitMinBlocks == r->minBlocksUsed && r->jitGmin == r->ctl.gmin)
+			r->jitMinBlocks == r->minBlocksUsed && r->jitGmin == r->ctl.gmin &&
+			r->jitMeasures == r->measures)
 		return 0;
-	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows, r->tpb,
-			r->minBlocksUsed, r->ctl.gmin);
+	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows,
+			r->measures, r->tpb, r->minBlocksUsed, r->ctl.gmin);
 	const std::string &key = src;
 	std::map<std::string, std::shared_ptr<JitKernel> >::iterator it = gKernelCache.find(key);
 	if (it != gKernelCache.end()) r->jit = it->second;
@@ -745,6 +749,7 @@ int buildJitKernel(simcu_ *r)
 		r->stats.jitCompiles++;
 	}
 	r->jitProbes = r->probeRows; r->jitTpb = r->tpb; r->jitMinBlocks = r->minBlocksUsed; r->jitGmin = r->ctl.gmin;
+	r->jitMeasures = r->measures;
 	return 0;
 }
 
@@ -808,6 +813,10 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 	if (r->dCI.reserve(CI_NUM * m4) || r->dRemaining.reserve(2 * sizeof(int)) ||
 			r->dOutGrid.reserve((size_t)r->ngrid * numProbes * m8))
 		return -1;
+	const int nmeas = (int)r->measures.size() / 2;
+	if (nmeas > 0 && r->interpreter) return fail("measures need the specialised kernel (interpreter = 0)");
+	if (r->dMeasure.reserve((size_t)std::max(1, nmeas) * m8) || r->dMeasureLevel.upload(r->measureLevels))
+		return -1;
 	if (r->rawMaxPoints > 0) {
 		if (r->rawCount < 1) { r->rawFirst = 0; r->rawCount = M; }
 		if (r->rawFirst < 0 || r->rawFirst + r->rawCount > M) return fail("raw_first/raw_count out of range");
@@ -830,6 +839,7 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		a.rawMaxPoints = r->rawMaxPoints; a.rawFirst = r->rawFirst; a.rawCount = r->rawCount;
 		a.CI = r->dCI.as<int>();
 		a.outGrid = r->dOutGrid.as<double>(); a.outRaw = r->dOutRaw.as<double>();
+		a.outMeasure = r->dMeasure.as<double>(); a.measureLevel = r->dMeasureLevel.as<double>();
 		a.attemptsPerLaunch = r->attemptsPerLaunch;
 		a.maxAttempts = (r->maxAttempts > 0) ? r->maxAttempts : LLONG_MAX;
 		a.remaining = r->dRemaining.as<int>();
@@ -1157,6 +1167,35 @@ int simcuGetStats(simcu_ *r, simcuStats_ *stats)
 	return 0;
 }
 
+int simcuSetMeasures(simcu_ *r, char *probes[], const int *kinds, const double *levels, int n)
+{
+	if (!r || n < 0 || (n > 0 && (!probes || !kinds))) return -1;
+	std::vector<int> m;
+	std::vector<double> lv;
+	for (int i = 0; i < n; i++) {
+		const int row = r->nl.findRow(probes[i]);
+		if (row < 1) return fail("unknown probe %s", probes[i] ? probes[i] : "(null)");
+		if (kinds[i] < MS_MIN || kinds[i] > MS_TCROSS_FALL) return fail("unknown measure kind %d", kinds[i]);
+		m.push_back(kinds[i]); m.push_back(row);
+		lv.push_back(levels ? levels[i] : 0.0);
+	}
+	r->measures = m; r->measureLevels = lv;
+	r->prepared = false;
+	return 0;
+}
+
+int simcuFetchMeasures(simcu_ *r, double *out)
+{
+	if (!r || !r->ran || !out) return -1;
+	const int n = (int)r->measures.size() / 2, M = r->M;
+	if (n == 0) return 0;
+	std::vector<double> tmp((size_t)n * M);
+	CU(cudaMemcpy(tmp.data(), r->dMeasure.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+	for (int i = 0; i < M; i++)
+		for (int q = 0; q < n; q++) out[(size_t)i * n + q] = tmp[(size_t)q * M + i];
+	return 0;
+}
+
 int simcuFetchCounters(simcu_ *r, char *which, int *out)
 {
 	if (!r || !r->ran || !which || !out) return -1;
@@ -1281,7 +1320,8 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	}
 	const int tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
 	const std::vector<double> consts[2] = {p.constOP, p.constTran};
-	const std::string src = assembleSource(p, sched, active, consts, probeRows, tpb, r->minBlocks, r->ctl.gmin);
+	const std::string src = assembleSource(p, sched, active, consts, probeRows, r->measures, tpb,
+			r->minBlocks, r->ctl.gmin);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;
 	std::string err;

@@ -553,8 +553,8 @@ void emitRows(Out &o, const char *name, const std::vector<int> &rows)
 
 }  /* namespace */
 
-std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock, int minBlocks,
-		double gmin)
+std::string generatePrelude(const Program &p, int numProbes, int numMeasures, int threadsPerBlock,
+		int minBlocks, double gmin)
 {
 	Out o;
 	o.f("#define SIMCU_JIT 1\n");
@@ -564,6 +564,7 @@ std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock
 			(int)p.pmap.size(), p.niinst, (int)p.histRows.size());
 	o.f("#define SIMCU_NPROBES %d\n#define SIMCU_TPB %d\n#define SIMCU_MINB %d\n", numProbes,
 			threadsPerBlock, minBlocks > 0 ? minBlocks : 1);
+	o.f("#define SIMCU_NMEASURES %d\n", numMeasures);
 	o.f("#define HUGE_VAL (__longlong_as_double(0x7ff0000000000000LL))\n");
 	o.f("#define SIMCU_GMIN (%s)\n", lit(gmin).c_str());
 	o.f("#define M_PI 3.14159265358979323846\n");
@@ -576,7 +577,7 @@ std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock
 
 std::string generateTopology(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
-		const std::vector<int> &probeRows)
+		const std::vector<int> &probeRows, const std::vector<int> &measures)
 {
 	Out o;
 	o.f("/* ---- generated for this netlist by simcu_codegen.cpp ---- */\n");
@@ -586,6 +587,12 @@ std::string generateTopology(const Program &p, const Schedule sched[2],
 	emitFactorSolve(o, p, sched[1], active[1], consts[1], 1);
 	emitRows(o, "genHistRows", p.histRows);
 	emitRows(o, "genProbeRows", probeRows);
+	/* measures: (kind, row) pairs; the level comes from the kernel arguments */
+	o.f("DEV void genMeasures(const Inst &c, double *meas, double tPrev, double tNow, bool first)\n{\n");
+	for (size_t q = 0; 2 * q + 1 < measures.size(); q++)
+		o.f("\tmeasureStep(c, %d, %d, __ldg(&c.a.measureLevel[%zu]), tPrev, tNow, first, meas[%zu]);\n",
+				measures[2 * q], measures[2 * q + 1], q, q);
+	o.f("\t(void)c; (void)meas; (void)tPrev; (void)tNow; (void)first;\n}\n\n");
 	return o.s;
 }
 

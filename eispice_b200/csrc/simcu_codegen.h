@@ -13,16 +13,16 @@
 namespace simcu {
 
 /* #defines of the topology's sizes; first part of the translation unit */
-std::string generatePrelude(const Program &p, int numProbes, int threadsPerBlock, int minBlocks,
-		double gmin);
+std::string generatePrelude(const Program &p, int numProbes, int numMeasures, int threadsPerBlock,
+		int minBlocks, double gmin);
 /* device records, expressions and the unrolled LU of both phases */
 std::string generateTopology(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
-		const std::vector<int> &probeRows);
+		const std::vector<int> &probeRows, const std::vector<int> &measures);
 /* prelude + embedded library headers + topology + kernel */
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
-		const std::vector<int> &probeRows,
+		const std::vector<int> &probeRows, const std::vector<int> &measures,
 		int threadsPerBlock, int minBlocks, double gmin);
 
 /* A compiled kernel.  compile() needs no GPU (NVRTC only); load() does. */

@@ -1236,6 +1236,34 @@ DEV double xOld(const Inst &c, int row)
 }
 #endif
 
+#ifdef SIMCU_JIT
+/* Device-side post-processing: one running measure of an
+ * unknown over the accepted steps, so a million-instance sweep can return a
+ * few numbers per instance instead of whole waveforms.  kind and row are
+ * compile-time constants of the specialised kernel; v is the measure's state.
+ * Crossing times interpolate linearly inside the accepted step, like the
+ * reference's own result access (module/circuit.py:48-67); NaN = never. */
+DEV void measureStep(const Inst &c, int kind, int row, double level, double tPrev, double tNow,
+		bool first, double &v)
+{
+	const double xN = xNew(c, row);
+	switch (kind) {
+	case MS_MIN: v = (first || xN < v) ? xN : v; break;
+	case MS_MAX: v = (first || xN > v) ? xN : v; break;
+	case MS_FINAL: v = xN; break;
+	default: {
+		if (first) { v = HUGE_VAL - HUGE_VAL; break; }       /* NaN: not crossed yet */
+		if (v == v) break;                                   /* first crossing only */
+		const double xP = xOld(c, row);
+		const bool hit = (kind == MS_TCROSS_RISE) ? (xP < level && xN >= level)
+			: (xP > level && xN <= level);
+		if (hit) v = tPrev + ((level - xP) / (xN - xP)) * (tNow - tPrev);
+		break;
+	}
+	}
+}
+#endif
+
 /* linear interpolation of the probes onto the tstep grid, exactly what
  * numpy.interp does on the adaptive waveform: for a grid time tg with
  * tPrev <= tg < tNow: slope * (tg - tPrev) + xPrev; a knot returns its value */

@@ -78,14 +78,15 @@ void jitSetNvrtcPath(const char *path) { gNvrtcHint = path ? path : ""; }
 
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
-		const std::vector<int> &probeRows,
+		const std::vector<int> &probeRows, const std::vector<int> &measures,
 		int threadsPerBlock, int minBlocks, double gmin)
 {
-	std::string s = generatePrelude(p, (int)probeRows.size(), threadsPerBlock, minBlocks, gmin);
+	std::string s = generatePrelude(p, (int)probeRows.size(), (int)measures.size() / 2,
+			threadsPerBlock, minBlocks, gmin);
 	s += kSrcProgram;
 	s += kSrcCalc;
 	s += kSrcDevice;
-	s += generateTopology(p, sched, active, consts, probeRows);
+	s += generateTopology(p, sched, active, consts, probeRows, measures);
 	s += kSrcJitKernel;
 	return s;
 }

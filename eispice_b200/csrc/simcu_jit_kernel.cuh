@@ -24,6 +24,7 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 	int hrows[SIMCU_DIM(SIMCU_NH)], prows[SIMCU_DIM(SIMCU_NPROBES)];
 	genHistRows(hrows);
 	genProbeRows(prows);
+	double meas[SIMCU_DIM(SIMCU_NMEASURES)];
 
 	/* parameters of this instance: broadcast constants or its own column */
 	SIMCU_UNROLL
@@ -91,6 +92,7 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 		if (!transient) {                               /* :126-137 */
 			if (count > k.itl1) { c.err = SIMCU_ERR_OP; break; }
 			gridOutput(c, prows, 0.0, 0.0, true);
+			genMeasures(c, meas, 0.0, 0.0, true);
 			SIMCU_UNROLL
 			for (int r = 0; r < SIMCU_N; r++) c.Xa[r] = c.Xv[r];
 			if (opOnly || !(0.0 < k.tstop)) { recordStep(c, hrows, 0.0); break; }
@@ -115,6 +117,7 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 				rejLte++;
 			} else {                                    /* accepted: :220-233 */
 				gridOutput(c, prows, prevTime, time, false);
+				genMeasures(c, meas, prevTime, time, false);
 				SIMCU_UNROLL
 				for (int r = 0; r < SIMCU_N; r++) c.Xa[r] = c.Xv[r];
 				order = (order < k.maxorder) ? order + 1 : order;
@@ -140,6 +143,8 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 		for (int r = 0; r < SIMCU_N; r++) c.Xv[r] = c.Xa[r];
 	}
 
+	SIMCU_UNROLL
+	for (int q = 0; q < SIMCU_NMEASURES; q++) a.outMeasure[(size_t)q * M + inst] = meas[q];
 	int *ci = a.CI + inst;
 	ci[(size_t)CI_STATUS * M] = c.err;
 	ci[(size_t)CI_DONE * M] = 1;

@@ -81,6 +81,9 @@ enum {
 #define CALC_MAX_VARS 16
 #define CALC_VAR_TIME (-2)   /* variable reference meaning "time" */
 
+/* device-side measures on a probe (simcuSetMeasures) */
+enum { MS_MIN = 0, MS_MAX, MS_FINAL, MS_TCROSS_RISE, MS_TCROSS_FALL };
+
 /* per-instance control scalars (doubles) */
 enum {
 	CD_TIME = 0, CD_PREVTIME, CD_THISSTEP, CD_MAXSTEP, CD_LTESTEP, CD_NUM
@@ -137,6 +140,8 @@ typedef struct {
 	double *Ht, *Hx;          /* T-line history: Hx[thread][R][1 + nh], column 0 = time */
 	double *outGrid;          /* [ngrid][nprobes][M] */
 	double *outRaw;           /* [rawMaxPoints][N+1][rawCount] */
+	double *outMeasure;       /* [nmeasures][M]: device-side post-processing */
+	const double *measureLevel; /* [nmeasures] threshold of the crossing measures */
 	double *wsGlobal;         /* [(F+N)][M] when the workspace is not in smem */
 	int wsShared;
 	int attemptsPerLaunch;

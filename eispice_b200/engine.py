@@ -96,6 +96,8 @@ def lib():
     L.simcuGetStats.argtypes = [vp, vp]
     L.simcuFetchRaw.argtypes = [vp, C.c_int, vp, ip, ip]
     L.simcuFetchCounters.argtypes = [vp, cp, vp]
+    L.simcuSetMeasures.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.simcuFetchMeasures.argtypes = [vp, vp]
     L.simcuNumUnknowns.argtypes = [vp]
     L.simcuNumNonzeros.argtypes = [vp]
     L.simcuGetPattern.argtypes = [vp, vp, vp]
@@ -135,6 +137,8 @@ class BatchResult:
 
 
 def output_grid(tstep, tstop, ngrid):
+    if ngrid <= 0:
+        return np.zeros(0)
     g = np.arange(ngrid, dtype=np.float64) * tstep
     g[-1] = tstop
     return np.minimum(g, tstop)
@@ -367,6 +371,27 @@ class Engine:
     def device_output_ptr(self):
         return self.L.simcuDeviceOutput(self.h)
 
+    MEASURE_KINDS = {"min": 0, "max": 1, "final": 2, "tcross_rise": 3, "tcross_fall": 4}
+
+    def set_measures(self, measures):
+        """[(probe, kind[, level]), ...] -> device-side post-processing of the
+        accepted steps; kind is min, max, final, tcross_rise or tcross_fall."""
+        measures = list(measures or [])
+        n = len(measures)
+        names = self._probe_array([m[0] for m in measures])
+        kinds = np.array([self.MEASURE_KINDS[m[1]] for m in measures], dtype=np.int32)
+        levels = np.array([float(m[2]) if len(m) > 2 else 0.0 for m in measures], dtype=np.float64)
+        if self.L.simcuSetMeasures(self.h, names, kinds.ctypes.data, levels.ctypes.data, n):
+            raise KeyError("bad measure list")
+        self._nmeasures = n
+
+    def fetch_measures(self):
+        n = getattr(self, "_nmeasures", 0)
+        out = np.empty((self.num_instances, n), dtype=np.float64)
+        if n and self.L.simcuFetchMeasures(self.h, out.ctypes.data):
+            raise RuntimeError("simcuFetchMeasures failed")
+        return out
+
     def counters(self, which):
         """Per-instance counter array of the last batch ('accepted', 'factorizations', ...)."""
         out = np.empty(self.num_instances, dtype=np.int32)
@@ -383,17 +408,22 @@ class Engine:
         self.L.simcuFree(data)
         return arr
 
-    def tran_batch(self, tstep, tstop, tmax=0.0, params=None, probes=(), **options):
+    def tran_batch(self, tstep, tstop, tmax=0.0, params=None, probes=(), measures=None,
+                   **options):
         for k, v in options.items():
             self.set_option(k, v)
+        if measures is not None:
+            self.set_measures(measures)
         if params:
             self.set_params(params)
         self.prepare(tstep, tstop, tmax, probes)
         self.upload()
         self.run_device()
         data, status = self.fetch()
-        return BatchResult(data, output_grid(tstep, tstop, self.ngrid), status,
-                           self.stats(), probes)
+        res = BatchResult(data, output_grid(tstep, tstop, self.ngrid), status,
+                          self.stats(), probes)
+        res.measures = self.fetch_measures()      # [M, nmeasures]
+        return res
 
     def compile_only(self, probes=()):
         """(source text, cubin bytes) of the topology-specialised kernel; needs

@@ -185,6 +185,15 @@ int simcuNumGrid(simcu_ *r);
 /* device pointer of the gridded output, layout [numGrid][numProbes][M] */
 void *simcuDeviceOutput(simcu_ *r);
 int simcuGetStats(simcu_ *r, simcuStats_ *stats);
+/* Device-side post-processing (eispice NOTES:40 "Add post-processors"): n
+ * running measures, each on one unknown probes[i] ("v(node)" / "i(refdes)"),
+ * kinds[i] = 0 minimum, 1 maximum, 2 final value, 3 / 4 time of the first
+ * rising / falling crossing of levels[i] (linear interpolation inside the
+ * accepted step, NaN if it never crosses).  Evaluated over the accepted steps
+ * inside the transient kernel; simcuFetchMeasures copies [numInstances][n] out.
+ * n = 0 switches them off. */
+int simcuSetMeasures(simcu_ *r, char *probes[], const int *kinds, const double *levels, int n);
+int simcuFetchMeasures(simcu_ *r, double *out);
 /* per-instance counters of the last batch into out[numInstances]; which is
  * status, accepted, rejected_lte, rejected_nc, factorizations or
  * op_factorizations */

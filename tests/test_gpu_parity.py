@@ -433,3 +433,37 @@ def test_history_ring_overflow_is_retried_with_a_deeper_ring():
             tol = parity.RELTOL * np.abs(ref).max() + (parity.VNTOL if name[0] == "v" else parity.ABSTOL)
             assert np.abs(res.data[i, :, p] - ref).max() < tol, (i, name)
     eng.close()
+
+
+def test_device_side_measures_equal_post_processing_of_the_raw_record():
+    """min / max / final / first threshold crossings computed inside the kernel
+    over the accepted steps == the same quantities computed on the host from the
+    instance's raw record."""
+    w = workloads.make("cfg1", 64)
+    meas = [("v(out)", "max"), ("v(out)", "min"), ("v(out)", "final"),
+            ("v(out)", "tcross_rise", 0.5), ("v(out)", "tcross_fall", 0.5),
+            ("i(V1)", "min"), ("v(out)", "tcross_rise", 5.0)]
+    eng = engine.Engine(w.cct.netlist(), w.M)
+    res = eng.tran_batch(w.tstep, w.tstop, 0.0, w.params, [], measures=meas,
+                         raw_max_points=4000, raw_count=w.M)
+    assert (res.status == 0).all() and res.measures.shape == (w.M, len(meas))
+    names = eng.variables()
+    for i in range(0, w.M, 7):
+        raw = eng.fetch_raw(i)
+        t, v, cur = raw[:, 0], raw[:, names.index("v(out)")], raw[:, names.index("i(V1)")]
+
+        def cross(level, rising):
+            for k in range(1, len(t)):
+                hit = (v[k - 1] < level <= v[k]) if rising else (v[k - 1] > level >= v[k])
+                if hit:
+                    return t[k - 1] + ((level - v[k - 1]) / (v[k] - v[k - 1])) * (t[k] - t[k - 1])
+            return float("nan")
+        want = [v.max(), v.min(), v[-1], cross(0.5, True), cross(0.5, False), cur.min(),
+                cross(5.0, True)]
+        got = res.measures[i]
+        assert np.isnan(got[6]) and np.isnan(want[6])
+        np.testing.assert_allclose(got[:6], want[:6], rtol=1e-12, atol=0)
+    # measures are per probe list: a second run without them returns none
+    res2 = eng.tran_batch(w.tstep, w.tstop, 0.0, w.params, ["v(out)"], measures=[])
+    assert res2.measures.shape == (w.M, 0) and res2.data.shape[2] == 1
+    eng.close()
