@@ -149,6 +149,15 @@ class Circuit:
         return eng.tran_batch(units.float(tstep), units.float(tstop),
                               units.float(tmax), params, probes or [], **options)
 
+    def op_batch(self, params=None, probes=None, num_instances=None):
+        """Operating point of every instance of a sweep: ([M, nprobes], status[M])."""
+        params = params or {}
+        if num_instances is None:
+            sizes = {len(np.atleast_1d(v)) for v in params.values()}
+            num_instances = max(sizes) if sizes else 1
+        eng = self._get_engine(int(num_instances))
+        return eng.op_batch(list(probes or []), params)
+
     # -- result access (reference circuit.py:140-190,241-298) ---------------
     def _results(self):
         res = self.results

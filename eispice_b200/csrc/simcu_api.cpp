@@ -1241,6 +1241,36 @@ int simcuRunTransientBatch(simcu_ *r, double tstep, double tstop, double tmax, i
 	return 0;
 }
 
+/* Operating point of every instance: the requested
+ * unknowns come back through the measure path (kind "final" at the OP). */
+int simcuRunOperatingPointBatch(simcu_ *r, char *probes[], int numProbes, double *data[],
+		int *status[])
+{
+	if (!r || numProbes < 1 || !probes || !data) return -1;
+	const std::vector<int> saveM = r->measures;
+	const std::vector<double> saveL = r->measureLevels;
+	std::vector<int> kinds(numProbes, MS_FINAL);
+	int rc = simcuSetMeasures(r, probes, kinds.data(), nullptr, numProbes);
+	double *out = nullptr;
+	int *st = nullptr;
+	if (!rc) rc = prepare(r, 0.0, 0.0, 0.0, nullptr, 0, true);
+	if (!rc) rc = runDevice(r, 0, true);
+	if (!rc) {
+		out = (double *)std::malloc(sizeof(double) * (size_t)r->M * numProbes);
+		st = status ? (int *)std::malloc(sizeof(int) * r->M) : nullptr;
+		if (!out || (status && !st)) rc = fail("out of memory");
+	}
+	if (!rc) rc = simcuFetchMeasures(r, out);
+	if (!rc && st && cudaMemcpy(st, r->dCI.as<int>() + (size_t)CI_STATUS * r->M, (size_t)r->M * 4,
+			cudaMemcpyDeviceToHost) != cudaSuccess)
+		rc = fail("status download failed");
+	r->measures = saveM; r->measureLevels = saveL; r->prepared = false;
+	if (rc) { std::free(out); std::free(st); return -1; }
+	*data = out;
+	if (status) *status = st;
+	return 0;
+}
+
 int simcuRunTransient(simcu_ *r, double tstep, double tstop, double tmax, int restart,
 		int instance, double *data[], char **variables[], int *numPoints, int *numVariables)
 {

@@ -84,6 +84,7 @@ def lib():
     L.simcuRunTransient.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int,
                                     C.c_int, vp, vp, ip, ip]
     L.simcuRunOperatingPoint.argtypes = [vp, C.c_int, vp, vp, ip, ip]
+    L.simcuRunOperatingPointBatch.argtypes = [vp, vp, C.c_int, vp, vp]
     L.simcuRunTransientBatch.argtypes = [vp, C.c_double, C.c_double, C.c_double,
                                          C.c_int, vp, C.c_int, vp, ip, vp, vp]
     L.simcuPrepare.argtypes = [vp, C.c_double, C.c_double, C.c_double, vp, C.c_int]
@@ -333,6 +334,22 @@ class Engine:
         rc = self.L.simcuRunOperatingPoint(self.h, instance, C.byref(data), C.byref(names),
                                            C.byref(npts), C.byref(nvar))
         return self._collect(rc, data, names, npts, nvar)
+
+    def op_batch(self, probes, params=None):
+        """Operating point of every instance: ([M, nprobes] values, [M] status)."""
+        if params:
+            self.set_params(params)
+        data, status = C.POINTER(C.c_double)(), C.POINTER(C.c_int)()
+        n = len(probes)
+        if self.L.simcuRunOperatingPointBatch(self.h, self._probe_array(probes), n,
+                                              C.byref(data), C.byref(status)):
+            raise RuntimeError("simcuRunOperatingPointBatch failed")
+        M = self.num_instances
+        out = np.ctypeslib.as_array(data, shape=(M, n)).copy()
+        st = np.ctypeslib.as_array(status, shape=(M,)).copy()
+        self.L.simcuFree(data)
+        self.L.simcuFree(status)
+        return out, st
 
     # -- batched runs ----------------------------------------------------------------
     def _probe_array(self, probes):

@@ -157,6 +157,11 @@ int simcuRunTransient(simcu_ *r, double tstep, double tstop, double tmax,
 int simcuRunOperatingPoint(simcu_ *r, int instance, double *data[],
 		char **variables[], int *numPoints, int *numVariables);
 
+/* Operating point of every instance: *data is malloc'd
+ * [numInstances][numProbes], *status (optional) malloc'd [numInstances]. */
+int simcuRunOperatingPointBatch(simcu_ *r, char *probes[], int numProbes,
+		double *data[], int *status[]);
+
 /* Batched transient, HOST buffers in and out (the e2e path): uploads the
  * per-instance parameters, runs every instance with its own adaptive step
  * control, resamples the probes onto the grid t_g = g*tstep (g = 0..numGrid-1,

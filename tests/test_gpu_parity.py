@@ -467,3 +467,18 @@ def test_device_side_measures_equal_post_processing_of_the_raw_record():
     res2 = eng.tran_batch(w.tstep, w.tstop, 0.0, w.params, ["v(out)"], measures=[])
     assert res2.measures.shape == (w.M, 0) and res2.data.shape[2] == 1
     eng.close()
+
+
+def test_operating_point_batch():
+    """OP of a whole sweep in one launch equals the per-instance OP runs and the
+    reference's doctest table (module/device.py:462-473)."""
+    cct = circuits.vi_table()
+    dc = np.array([10.0, -5.0, 0.0, 1.0, 5.0, 12.0])
+    vals, status = cct.op_batch({"Vx.DC": dc}, ["i(VIx)", "v(1)"])
+    assert (status == 0).all() and vals.shape == (6, 2)
+    np.testing.assert_allclose(vals[:, 0], [10.0, -2.0, 1.0, 3.0, 8.0, 8.0], rtol=1e-6)
+    np.testing.assert_allclose(vals[:, 1], dc, rtol=0, atol=1e-12)
+    eng = cct._engine
+    for i in (1, 4):
+        one, var = eng.op_single(instance=i)
+        assert one[0, var.index("i(VIx)")] == vals[i, 0]
