@@ -451,6 +451,7 @@ struct Flattener {
 	{
 		if (!src || !*src || !len || *len < 1) { err = "missing table"; return false; }
 		const int n = *len;
+		if (type == 'c' && n < 2) { err = "a spline table needs at least two points"; return false; }
 		const double *xy = *src;
 		id = (int)p.tabType.size();
 		std::vector<double> x(n), y(n), m(n, 0.0);
