@@ -40,6 +40,23 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 METRIC = "instance-timesteps/sec batched transient"
 UNIT = "instance-timesteps/s"
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout must carry the one JSON line only: libraries that print to fd 1
+    (NCCL's version banner, simcuInfo, ...) are sent to stderr from here on."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 # ---------------------------------------------------------------------------
 # CPU reference arm (test infrastructure: oracle/_ref, else the oracle port)
@@ -117,7 +134,7 @@ def run_reference_arm(a):
                              "sample": "per step: " + sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -222,6 +239,7 @@ def main():
     ap.add_argument("--minblocks", type=int, default=0)
     ap.add_argument("--maxblocks", type=int, default=0)
     a = ap.parse_args()
+    _claim_stdout()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
     if a.impl == "reference":
@@ -242,9 +260,6 @@ def main():
     engine.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's own log lines (e.g. its version banner) go to stderr, so that
-        # stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -398,7 +413,7 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0,
                                         "kind": "port", "sample": "failed: %s" % e}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
