@@ -385,3 +385,81 @@ def test_generated_lu_solves_the_system(name, tmp_path):
         want = np.linalg.solve(dense, b)
         assert np.allclose(x, want, rtol=1e-8, atol=1e-9 * np.abs(want).max()), (name, phase)
     eng.close()
+
+
+# ---- generated expression code: compile genCalc / genCalcGrad for the HOST and
+# ---- compare with the bytecode interpreter (itself pinned to the reference) ----
+def _host_calc_harness(src, tmp_path, n_unknowns):
+    import ctypes as C
+    import subprocess
+    gmin = re.search(r"#define SIMCU_GMIN \((.*)\)", src).group(1)
+    start = src.index("DEV void genCalc(Inst &c, int id, int dvar, double &f, double &dv)\n{")
+    end = src.index("DEV void genLoad(Inst &c)")
+    body = src[start:end]
+    calc_h = open(os.path.join(ROOT, "eispice_b200", "csrc", "simcu_calc.h")).read()
+    prog_h = open(os.path.join(ROOT, "eispice_b200", "csrc", "simcu_program.h")).read()
+    calc_h = "\n".join(ln for ln in calc_h.splitlines() if not ln.lstrip().startswith("#include"))
+    code = """
+#include <cmath>
+#include <cstring>
+%s
+%s
+#define DEV static inline
+#define SIMCU_GMIN (%s)
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+struct Inst { double x[%d]; double time; double X(int row) const { return row ? x[row] : 0.0; } };
+%s
+extern "C" void eval(int id, int nvars, const double *x, double time, double *f, double *g, double *g1)
+{
+	Inst c; std::memcpy(c.x, x, sizeof c.x); c.time = time;
+	double dv;
+	genCalc(c, id, -1, *f, dv);
+	genCalcGrad(c, id, g);
+	for (int v = 0; v < nvars; v++) { double ff; genCalc(c, id, v, ff, g1[v]); }
+}
+""" % (prog_h, calc_h, gmin, n_unknowns + 1, body)
+    cpp = tmp_path / "calc.cpp"
+    so = tmp_path / "calc.so"
+    cpp.write_text(code)
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cpp)],
+                   check=True)
+    return C.CDLL(str(so))
+
+
+@pytest.mark.parametrize("name", ["cfg2_rectifier", "b_current", "b_capacitor", "cfg3_oscillator",
+                                  "b_voltage_time", "cccs"])
+def test_generated_expression_code_equals_the_interpreter(name, tmp_path):
+    import ctypes as C
+    build = circuits.all_cases()[name][0]
+    nl = build().netlist()
+    eng = engine.Engine(nl, 1)
+    names = eng.variables()                    # names[row], row 0 = "time" stands for ground here
+    src, _ = eng.compile_only(names[1:2])
+    lib = _host_calc_harness(src, tmp_path, len(names) - 1)
+    exprs = [d[5] for d in nl if d[0] == "B"]
+    cases = re.findall(r"\tcase (\d+): \{\n((?:\t\tconst double v\d+ = [^\n]+\n)*)\t\tswitch \(dvar\)", src)
+    assert len(cases) == len(exprs)
+    rng = np.random.default_rng(4)
+    for (cid, decl), expr in zip(cases, exprs):
+        refs = re.findall(r"const double v(\d+) = (c\.time|c\.X\((\d+)\));", decl)
+        var_names = ["time" if r[1] == "c.time" else names[int(r[2])] for r in refs]
+        for _ in range(25):
+            x = np.zeros(len(names))
+            x[1:] = rng.uniform(-2.0, 2.0, len(names) - 1)
+            t = float(rng.uniform(0, 1e-8))
+            vals = [t if v == "time" else x[names.index(v)] for v in var_names]
+            rc, want_f, want_d = engine.calc_eval(expr, var_names, vals)
+            f = C.c_double()
+            g = (C.c_double * 16)(*([float("nan")] * 16))
+            g1 = (C.c_double * 16)()
+            lib.eval(int(cid), len(var_names), x.ctypes.data_as(C.c_void_p), C.c_double(t),
+                     C.byref(f), g, g1)
+            if rc != 0:
+                continue                       # NaN somewhere: both sides flag it
+            assert _same(f.value, want_f), (expr, vals, f.value, want_f)
+            for k, v in enumerate(var_names):
+                if v == "time":
+                    continue
+                assert _same(g[k], want_d[k]), (expr, v, g[k], want_d[k])
+                assert _same(g1[k], want_d[k]), (expr, v, g1[k], want_d[k])
+    eng.close()
