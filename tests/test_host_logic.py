@@ -463,3 +463,42 @@ def test_generated_expression_code_equals_the_interpreter(name, tmp_path):
                 assert _same(g[k], want_d[k]), (expr, v, g[k], want_d[k])
                 assert _same(g1[k], want_d[k]), (expr, v, g1[k], want_d[k])
     eng.close()
+
+
+def test_b_source_variables_create_rows_in_order_of_appearance():
+    """A B equation may mention unknowns that no device has created yet: rows
+    appear in order of first mention inside the equation
+    (devices/nonlinear_i.c:147-192, core/row.c:163-204), and the Jacobian
+    entries join the pattern."""
+    import eispice_b200 as eispice
+    cct = circuits._new("order")
+    cct.Bx = eispice.B('out', 0, eispice.Current, "v(later) * 2 + i(Vz) + v(out)")
+    cct.Rz = eispice.R('later', 0, 10)
+    cct.Vz = eispice.V('later', 0, 1)
+    cct.Ro = eispice.R('out', 0, 5)
+    nl = cct.netlist()
+    eng = engine.Engine(nl, 1)
+    assert eng.variables() == backends.OracleSim(nl).op()[1]
+    assert eng.variables()[:6] == ["time", "v(out)", "i(Bx)", "v(Bx)", "v(later)", "i(Vz)"]
+    n, ri, cs = eng.pattern()
+    n2, ri2, cs2 = backends.OracleSim(nl).pattern()
+    assert np.array_equal(ri, ri2) and np.array_equal(cs, cs2)
+    eng.close()
+
+
+def test_measure_and_probe_names_are_checked_on_the_host():
+    import ctypes as C
+    L = engine.lib()
+    L.simcuSetOption(None, b"quiet", 1.0)
+    try:
+        eng = engine.Engine(circuits.cfg1_rc().netlist(), 4)
+        with pytest.raises(KeyError):
+            eng.set_measures([("v(nowhere)", "max")])
+        with pytest.raises(KeyError):
+            eng.set_measures([("v(out)", "median")])
+        eng.set_measures([("v(out)", "max"), ("i(V1)", "tcross_fall", -1e-3)])
+        src, _ = eng.compile_only(["v(out)"])
+        assert "#define SIMCU_NMEASURES 2" in src and src.count("measureStep(c, ") == 2
+        eng.close()
+    finally:
+        L.simcuSetOption(None, b"quiet", 0.0)
