@@ -118,3 +118,23 @@ def test_parameter_sweep_matches_rebuild():
     cct.R1.R = 2.5e3
     d2, _ = backends.OracleSim(cct.netlist()).tran(0.01e-9, 10e-9)
     np.testing.assert_array_equal(d1, d2)
+
+
+@pytest.mark.skipif(not backends.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("cfg,index", [("cfg2", 17), ("cfg3", 5), ("cfg4", 4), ("cfg4", 9), ("cfg5", 2)])
+def test_oracle_matches_live_reference_on_sweep_instances(cfg, index):
+    """The oracle is pinned on the SWEEP space too: instances of the synthetic
+    workloads (random parameters, non-typical IBIS corners, falling edges) run on
+    the unmodified reference and on the oracle."""
+    import workloads
+    w = workloads.make(cfg, 24)
+    nl, s = w.instance_netlist(index)
+    do, vo = backends.OracleSim(nl, s).tran(w.tstep, w.tstop)
+    dr, vr = backends.RefSim(nl, s).tran(w.tstep, w.tstop)
+    assert vo == vr
+    do, dr = parity.drop_degenerate(do, w.tstep), parity.drop_degenerate(dr, w.tstep)
+    worst = parity.grid_error(do[:, 0], do, dr[:, 0], dr, vo, w.tstep, w.tstop, current_floor=1e-3)
+    assert worst < 5.0, "grid error %.3g x SPICE tolerance" % worst
+    if do.shape == dr.shape and cfg != "cfg2":     # cfg2 is SEQUENCE_SENSITIVE (see top)
+        frac, tight = parity.tight_fraction(do, dr)
+        assert frac >= 0.98, (frac, tight)
