@@ -468,6 +468,11 @@ void emitPhases(Out &o, const Program &p)
 		"\treturn linear;\n}\n\n", "}\n\n", "}\n\n"};
 	for (int ph = 0; ph < 7; ph++) {
 		o.f("%s", head[ph]);
+		if (ph == 3) {          /* integrate: the shared time ring advances once */
+			bool any = false;
+			for (int k = 0; k < p.ndev; k++) any = any || inPhase(&p.dev[(size_t)k * SIMCU_DEV_STRIDE], 3);
+			if (any) o.f("\titBegin(c);\n");
+		}
 
 		for (int k = 0; k < p.ndev; k++) {
 			if (!inPhase(&p.dev[(size_t)k * SIMCU_DEV_STRIDE], ph)) continue;

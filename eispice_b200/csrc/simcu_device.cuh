@@ -66,6 +66,12 @@ struct Inst {
 	mutable double Xv[SIMCU_DIM(SIMCU_N)], Xa[SIMCU_DIM(SIMCU_N)];
 	mutable double sv[SIMCU_DIM(SIMCU_SD)];
 	mutable int iv[SIMCU_DIM(SIMCU_SI)];
+	/* time and step rings of the integrators: every C / L / nonlinear C of an
+	 * instance is initialised and stepped at the same times, so the reference's
+	 * per-device copies (integrator.c:44-57) hold identical values - one copy */
+	mutable double itT[4], itH[3];
+	mutable int itN;
+	mutable bool itAdv;
 	double par[SIMCU_DIM(SIMCU_NPARAM)];
 	int tset[SIMCU_DIM(SIMCU_NISET)];
 
@@ -337,34 +343,48 @@ enum { RT = 0, RH = 1, RX = 2, RY = 3, RF = 4 };
 
 DEV void itInitialize(const Inst &c, int sb, int ib, double ic, double ydtdx)
 {
-	c.S(sb) = 0.0; c.S(sb + 1) = 0.0; c.IS(ib) = 0;
+	(void)ib;
+	c.S(sb) = 0.0; c.S(sb + 1) = 0.0;
+	c.itN = 0; c.itAdv = false;
 	SIMCU_UNROLL
 	for (int j = 0; j < 4; j++) {
-		AGE(c, sb, RT, j) = 0.0; AGE(c, sb, RH, j) = c.a.ctl.tstop;
+		c.itT[j] = 0.0;
 		AGE(c, sb, RY, j) = 0.0; AGE(c, sb, RX, j) = ic; AGE(c, sb, RF, j) = ydtdx;
 	}
+	SIMCU_UNROLL
+	for (int j = 0; j < 3; j++) c.itH[j] = c.a.ctl.tstop;
+}
+
+/* once per attempt, before the devices integrate: advance the shared time ring
+ * if time moved on (integrator.c:124-126) and note the step */
+DEV void itBegin(const Inst &c)
+{
+	const double t0 = c.time;
+	c.itAdv = (t0 > c.itT[3]);
+	if (c.itAdv) {
+		c.itN++;
+		const double tNext = c.itT[3];
+		c.itT[3] = c.itT[2]; c.itT[2] = c.itT[1]; c.itT[1] = c.itT[0]; c.itT[0] = tNext;
+		c.itH[2] = c.itH[1]; c.itH[1] = c.itH[0];
+	}
+	c.itH[0] = t0 - c.itT[0];
+	c.itT[3] = t0;
 }
 
 /* integrator.c:106-163 */
 DEV void itIntegrate(Inst &c, int sb, int ib, double x0, double ydtdx,
 		double &dydx0, double &y0)
 {
+	(void)ib;
 	if (isnan(x0)) { c.err = SIMCU_ERR_NAN; return; }
-	const double t0 = c.time;
-	int nn = c.IS(ib);
-	if (t0 > AGE(c, sb, RT, 3)) {
-		nn++; c.IS(ib) = nn;
-		const double tNext = AGE(c, sb, RT, 3);
-		AGE(c, sb, RT, 3) = AGE(c, sb, RT, 2); AGE(c, sb, RT, 2) = AGE(c, sb, RT, 1);
-		AGE(c, sb, RT, 1) = AGE(c, sb, RT, 0); AGE(c, sb, RT, 0) = tNext;
+	const int nn = c.itN;
+	if (c.itAdv) {
 		SIMCU_UNROLL
-		for (int k = RH; k <= RF; k++) {
+		for (int k = RX; k <= RF; k++) {
 			AGE(c, sb, k, 2) = AGE(c, sb, k, 1); AGE(c, sb, k, 1) = AGE(c, sb, k, 0);
 		}
 	}
-	const double h = t0 - AGE(c, sb, RT, 0);
-	AGE(c, sb, RH, 0) = h;
-	AGE(c, sb, RT, 3) = t0;
+	const double h = c.itH[0];
 	AGE(c, sb, RX, 0) = x0;
 	const double yn = c.S(sb + 1) * x0 - c.S(sb);
 	AGE(c, sb, RY, 0) = yn;
@@ -409,11 +429,15 @@ DEV double itNextStep(Inst &c, int sb, int ib, double x0, double ydtdx, double a
 {
 	if (isnan(x0)) { c.err = SIMCU_ERR_NAN; return 0.0; }
 	const SimcuControl &k = c.a.ctl;
-	const int nn = c.IS(ib);
+	const int nn = c.itN;
+	(void)ib;
+	/* below the counter the reference reads the same age of the PREVIOUS ring
+	 * (AGEQ): x <- h, h <- t, f <- y */
+	const double x1 = (nn >= 1) ? AGE(c, sb, RX, 1) : c.itH[1], x2 = (nn >= 2) ? AGE(c, sb, RX, 2) : c.itH[2];
+	const double h1 = (nn >= 1) ? c.itH[1] : c.itT[1], h2 = (nn >= 2) ? c.itH[2] : c.itT[2];
 	const double h = itNextStepFn(c.order, k.reltol, k.chgtol, k.trtol, abstol, x0, ydtdx,
-			c.S(sb), c.S(sb + 1), AGE(c, sb, RY, 0), AGE(c, sb, RH, 0), AGE(c, sb, RX, 0),
-			AGE(c, sb, RF, 0), AGEQ(c, sb, RF, 1, nn), AGEQ(c, sb, RX, 1, nn), AGEQ(c, sb, RH, 1, nn),
-			AGEQ(c, sb, RF, 2, nn), AGEQ(c, sb, RX, 2, nn), AGEQ(c, sb, RH, 2, nn));
+			c.S(sb), c.S(sb + 1), AGE(c, sb, RY, 0), c.itH[0], AGE(c, sb, RX, 0),
+			AGE(c, sb, RF, 0), AGEQ(c, sb, RF, 1, nn), x1, h1, AGEQ(c, sb, RF, 2, nn), x2, h2);
 	if (isnan(h)) c.err = SIMCU_ERR_NAN;
 	return h;
 }

@@ -44,6 +44,11 @@ DEV void jitRunInstance(const SimcuArgs &a, int inst, int slot, size_t hstride, 
 	for (int s = 0; s < SIMCU_SD; s++) c.sv[s] = 0.0;
 	SIMCU_UNROLL
 	for (int s = 0; s < SIMCU_SI; s++) c.iv[s] = 0;
+	c.itN = 0; c.itAdv = false;
+	SIMCU_UNROLL
+	for (int j = 0; j < 4; j++) c.itT[j] = 0.0;
+	SIMCU_UNROLL
+	for (int j = 0; j < 3; j++) c.itH[j] = 0.0;
 
 	double time = 0.0, prevTime = 0.0, thisStep = 0.0, maxStep = 0.0, lteStep = 0.0;
 	int order = 1, brk = 0;
