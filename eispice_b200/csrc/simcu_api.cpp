@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -94,6 +95,9 @@ struct _simcu {
 	int numPilots = 8;
 	/* compiled state */
 	bool compiled = false, prepared = false, ran = false;
+	bool paramsChanged = false;     /* per-instance values differ from those the pivots were chosen on */
+	bool ranTransient = false;      /* a transient has completed (restart = 0 would continue it) */
+	int single = -1;                /* >= 0: the next launch processes this instance only */
 	Program prog;
 	Schedule sched[2];
 	std::vector<int> forcePc[2], forcePr[2];
@@ -105,8 +109,12 @@ struct _simcu {
 	int historyRetry = 0;           /* 1: re-run instances that outran the history ring */
 	int minBlocks = 0;              /* __launch_bounds__ second argument */
 	int maxBlocksPerSM = 0;         /* cap on resident blocks (0 = occupancy limit) */
-	int minBlocksUsed = 0, jitMinBlocks = -1;
-	double jitGmin = -1.0;
+	int minBlocksUsed = 0;
+	JitConfig jitCfg;               /* what r->jit was compiled with */
+	int replay = 0;                 /* test instrumentation: replay an attempt log */
+	int claimBelow = 31;            /* lane claiming policy of the specialised kernel */
+	std::vector<int> replayOff, replayFlag;
+	std::vector<double> replayTime;
 	std::vector<char> active[2];
 	std::vector<double> consts[2];      /* per phase: literal value of a slot, NaN = varies */
 	std::vector<int> orderKey;          /* table-set indices the processing order was built from */
@@ -115,13 +123,14 @@ struct _simcu {
 	std::vector<int> jitMeasures;
 	std::shared_ptr<JitKernel> jit;
 	std::vector<int> jitProbes;
-	int jitTpb = 0, jitBlocks = 0, lanes = 32, lanesOpt = 0;
+	int jitBlocks = 0, lanes = 32, lanesOpt = 0;
 	SimcuArgs args[2];
 	simcuStats_ stats;
 	/* device memory */
 	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
 		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
-		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2, dMeasure, dMeasureLevel;
+		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2, dMeasure, dMeasureLevel,
+		dReplayOff, dReplayTime, dReplayFlag;
 	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dOutRaw, dWs, dRemaining;
 	int *hRemaining = nullptr;      /* pinned */
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -141,7 +150,7 @@ struct _simcu {
 	{
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
 			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder, &dOrder2, &dMeasure,
-			&dMeasureLevel, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
+			&dMeasureLevel, &dReplayOff, &dReplayTime, &dReplayFlag, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
 			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dOutRaw,
 			&dWs, &dRemaining};
 		for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) all[i]->release();
@@ -450,8 +459,15 @@ int simcuSetInstanceParam(simcu_ *r, char *refdes, char *name, const double *val
 	const bool isNew = !d->inst.count(n);
 	std::vector<double> &v = d->inst[n];
 	v.resize(r->M);
-	for (int i = 0; i < r->M; i++) v[i] = values[(size_t)i * stride];
+	bool changed = isNew;
+	for (int i = 0; i < r->M; i++) {
+		const double x = values[(size_t)i * stride];
+		changed = changed || std::memcmp(&v[i], &x, sizeof x) != 0;
+		v[i] = x;
+	}
 	if (isNew) { r->compiled = false; r->prepared = false; }
+	/* the pivot sequences were chosen on pilot instances of the old values */
+	if (changed) r->paramsChanged = true;
 	return 0;
 }
 
@@ -476,8 +492,14 @@ int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex, int s
 	if (!d || d->kind != DK_VI) return fail("%s is not a VI device", refdes);
 	const bool isNew = d->instSet.empty();
 	d->instSet.resize(r->M);
-	for (int i = 0; i < r->M; i++) d->instSet[i] = setIndex[(size_t)i * stride];
+	bool changed = isNew;
+	for (int i = 0; i < r->M; i++) {
+		const int x = setIndex[(size_t)i * stride];
+		changed = changed || d->instSet[i] != x;
+		d->instSet[i] = x;
+	}
 	if (isNew) { r->compiled = false; r->prepared = false; }
+	if (changed) r->paramsChanged = true;
 	return 0;
 }
 
@@ -510,6 +532,8 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "history_retry") r->historyRetry = (value != 0.0);
 	else if (n == "min_blocks_per_sm") { r->minBlocks = (int)value; r->jit.reset(); }
 	else if (n == "max_blocks_per_sm") r->maxBlocksPerSM = (int)value;
+	else if (n == "claim_below") r->claimBelow = std::max(0, std::min(31, (int)value));
+	else if (n == "replay") r->replay = (value != 0.0);
 	else return fail("unknown option %s", name);
 	r->prepared = false;
 	return 0;
@@ -522,6 +546,22 @@ int simcuSetPivots(simcu_ *r, int phase, const int *pc, const int *pr, int n)
 	if (pc && pr) {
 		r->forcePc[phase].assign(pc, pc + n);
 		r->forcePr[phase].assign(pr, pr + n);
+	}
+	r->prepared = false;
+	return 0;
+}
+
+int simcuSetReplayLog(simcu_ *r, const int *offsets, const double *times, const int *flags)
+{
+	if (!r) return -1;
+	r->replayOff.clear(); r->replayTime.clear(); r->replayFlag.clear();
+	if (offsets && times && flags) {
+		if (offsets[0] != 0) return fail("replay log: offsets[0] must be 0");
+		for (int i = 0; i < r->M; i++)
+			if (offsets[i + 1] < offsets[i]) return fail("replay log: offsets must not decrease");
+		r->replayOff.assign(offsets, offsets + r->M + 1);
+		r->replayTime.assign(times, times + offsets[r->M]);
+		r->replayFlag.assign(flags, flags + offsets[r->M]);
 	}
 	r->prepared = false;
 	return 0;
@@ -727,16 +767,20 @@ int pilotPass(simcu_ *r, bool needOP, bool needTran)
 
 /* process-wide cache of compiled topologies, keyed by the generated source */
 std::map<std::string, std::shared_ptr<JitKernel> > gKernelCache;
+std::mutex gKernelCacheLock;
+const size_t kKernelCacheMax = 64;      /* topologies kept loaded per process */
 
 int buildJitKernel(simcu_ *r)
 {
-	if (r->jit && r->jitProbes == r->probeRows && r->jitTpb == r->tpb &&
-			r->jitMinBlocks == r->minBlocksUsed && r->jitGmin == r->ctl.gmin &&
-			r->jitMeasures == r->measures)
+	JitConfig cfg;
+	cfg.threadsPerBlock = r->tpb; cfg.minBlocks = r->minBlocksUsed; cfg.gmin = r->ctl.gmin;
+	cfg.replay = r->replay;
+	if (r->jit && r->jitProbes == r->probeRows && r->jitCfg == cfg && r->jitMeasures == r->measures)
 		return 0;
 	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows,
-			r->measures, r->tpb, r->minBlocksUsed, r->ctl.gmin);
+			r->measures, cfg);
 	const std::string &key = src;
+	std::lock_guard<std::mutex> guard(gKernelCacheLock);
 	std::map<std::string, std::shared_ptr<JitKernel> >::iterator it = gKernelCache.find(key);
 	if (it != gKernelCache.end()) r->jit = it->second;
 	else {
@@ -744,11 +788,15 @@ int buildJitKernel(simcu_ *r)
 		std::string err;
 		if (!jitCompile(src, *k, err)) return fail("%s", err.c_str());
 		if (!jitLoad(*k, r->tpb, err)) return fail("%s", err.c_str());
+		/* bounded: drop entries no handle uses any more, oldest key first */
+		for (it = gKernelCache.begin(); it != gKernelCache.end() && gKernelCache.size() >= kKernelCacheMax;) {
+			if (it->second.use_count() == 1) it = gKernelCache.erase(it); else ++it;
+		}
 		gKernelCache[key] = k;
 		r->jit = k;
 		r->stats.jitCompiles++;
 	}
-	r->jitProbes = r->probeRows; r->jitTpb = r->tpb; r->jitMinBlocks = r->minBlocksUsed; r->jitGmin = r->ctl.gmin;
+	r->jitProbes = r->probeRows; r->jitCfg = cfg;
 	r->jitMeasures = r->measures;
 	return 0;
 }
@@ -848,14 +896,29 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 	}
 	if (uploadParameters(r, 0)) return -1;
 	if (uploadSchedule(r, 0) || uploadSchedule(r, 1)) return -1;
+	if (r->replay) {
+		if (r->interpreter) return fail("replay needs the specialised kernel (interpreter = 0)");
+		if ((int)r->replayOff.size() != M + 1) return fail("replay = 1 without a log (simcuSetReplayLog)");
+		if (r->dReplayOff.upload(r->replayOff) || r->dReplayTime.upload(r->replayTime) ||
+				r->dReplayFlag.upload(r->replayFlag))
+			return -1;
+	}
+	for (int ph = 0; ph < 2; ph++) {
+		SimcuArgs &a = r->args[ph];
+		a.claimBelow = r->claimBelow;
+		a.replayOff = r->dReplayOff.as<int>(); a.replayTime = r->dReplayTime.as<double>();
+		a.replayFlag = r->dReplayFlag.as<int>();
+	}
 	int sms = 148, dev = 0;
 	CU(cudaGetDevice(&dev));
 	CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
 	/* symbolic analysis on the pilot batch (one-off per topology and time scale) */
-	const bool needOP = r->sched[0].lu.empty() || !r->forcePc[0].empty();
-	const bool needTran = !opOnly && (r->sched[1].lu.empty() || runChanged || !r->forcePc[1].empty());
+	const bool needOP = r->sched[0].lu.empty() || !r->forcePc[0].empty() || r->paramsChanged;
+	const bool needTran = !opOnly && (r->sched[1].lu.empty() || runChanged || !r->forcePc[1].empty() ||
+			r->paramsChanged);
 	if ((needOP || needTran) && pilotPass(r, needOP, needTran)) return -1;
+	r->paramsChanged = false;
 	if (opOnly && r->sched[1].lu.empty()) {
 		r->sched[1] = r->sched[0]; r->active[1] = r->active[0]; r->consts[1] = r->consts[0];
 		if (uploadSchedule(r, 1)) return -1;
@@ -934,6 +997,9 @@ int runDevice(simcu_ *r, cudaStream_t st, bool opOnly)
 	CU(cudaEventRecord(r->ev0, st));
 	if (r->interpreter) {
 		if (resetState(r, st)) return -1;
+		/* an instance that fails keeps NaN from the failure time on (all-ones = NaN) */
+		if (r->ngrid > 0 && !r->probeRows.empty())
+			CU(cudaMemsetAsync(r->dOutGrid.p, 0xff, (size_t)r->ngrid * r->probeRows.size() * r->M * 8, st));
 		if (simcuLaunchLoad(&r->args[0], 128, st)) return fail("load kernel launch failed");
 		if (simcuLaunchOp(&r->args[0], r->tpb, opOnly ? 1 : 0, st)) return fail("op kernel launch failed");
 		launches += 2;
@@ -950,14 +1016,22 @@ int runDevice(simcu_ *r, cudaStream_t st, bool opOnly)
 		CU(cudaMemsetAsync(r->dRemaining.p, 0, 2 * sizeof(int), st));
 		CU(cudaEventRecord(r->ev2, st));
 		int op = opOnly ? 1 : 0;
-		r->args[1].count = r->M;
-		void *params[] = {(void *)&r->args[1], (void *)&op};
-		cudaError_t e = cudaLaunchKernel((const void *)r->jit->kernel, dim3(r->jitBlocks), dim3(r->tpb),
+		SimcuArgs a1 = r->args[1];
+		a1.count = r->M;
+		int blocks = r->jitBlocks;
+		if (r->single >= 0) {
+			/* simcuRunTransient / simcuRunOperatingPoint: one instance of the batch */
+			std::vector<int> one(1, r->single);
+			if (r->dOrder2.upload(one, st)) return -1;
+			a1.order = r->dOrder2.as<int>(); a1.count = 1; blocks = 1;
+		}
+		void *params[] = {(void *)&a1, (void *)&op};
+		cudaError_t e = cudaLaunchKernel((const void *)r->jit->kernel, dim3(blocks), dim3(r->tpb),
 				params, 0, st);
 		if (e != cudaSuccess) return fail("specialised kernel launch failed: %s", cudaGetErrorString(e));
 		launches = 1;
 		r->stats.historyRetries = 0;
-		if (!opOnly && r->histRecords > 0 && r->historyRetry) {
+		if (!opOnly && r->histRecords > 0 && r->historyRetry && r->single < 0) {
 			/* Instances that outran the T-line history ring (a burst of tiny steps
 			 * longer than the ring inside one line delay) run again on their own:
 			 * the same ring memory shared by few threads is orders of magnitude
@@ -1009,6 +1083,7 @@ int runDevice(simcu_ *r, cudaStream_t st, bool opOnly)
 	CU(cudaEventElapsedTime(&ms, r->ev2, r->ev1));
 	r->stats.tranMs = ms;
 	r->ran = true;
+	if (!opOnly) r->ranTransient = true;
 	return 0;
 }
 
@@ -1019,15 +1094,19 @@ int collectStats(simcu_ *r)
 	CU(cudaMemcpy(ci.data(), r->dCI.p, ci.size() * sizeof(int), cudaMemcpyDeviceToHost));
 	simcuStats_ &s = r->stats;
 	s.accepted = s.rejectedLTE = s.rejectedNC = s.factorizations = s.opFactorizations = s.failed = 0;
-	s.pivotBreakdowns = 0;
+	s.pivotBreakdowns = 0; s.replayDiffs = 0;
 	for (int i = 0; i < M; i++) {
+		if (r->single >= 0 && i != r->single) continue;
 		s.accepted += ci[(size_t)CI_ACCEPTED * M + i];
 		s.rejectedLTE += ci[(size_t)CI_REJ_LTE * M + i];
 		s.rejectedNC += ci[(size_t)CI_REJ_NC * M + i];
 		s.factorizations += ci[(size_t)CI_NFACT * M + i];
 		s.opFactorizations += ci[(size_t)CI_NFACT_OP * M + i];
 		s.failed += (ci[(size_t)CI_STATUS * M + i] != 0);
-		if (!r->interpreter) s.pivotBreakdowns += ci[(size_t)CI_BREAK * M + i];
+		if (!r->interpreter) {
+			s.pivotBreakdowns += ci[(size_t)CI_BREAK * M + i];
+			s.replayDiffs += ci[(size_t)CI_REPLAY_DIFF * M + i];
+		}
 	}
 	const Program &p = r->prog;
 	s.numUnknowns = p.N; s.numNonzeros = p.nnzA;
@@ -1096,7 +1175,9 @@ int runSingle(simcu_ *r, bool opOnly, double tstep, double tstop, double tmax, i
 		r->rawMaxPoints = cap; r->rawFirst = instance; r->rawCount = 1;
 		r->prepared = false;
 		if (prepare(r, tstep, tstop, tmax, nullptr, 0, opOnly)) break;
-		if (runDevice(r, 0, opOnly)) break;
+		r->single = r->interpreter ? -1 : instance;     /* launch that instance alone */
+		const int rcRun = runDevice(r, 0, opOnly);
+		if (rcRun) { r->single = -1; break; }
 		int status = 0;
 		if (cudaMemcpy(&status, r->dCI.as<int>() + (size_t)CI_STATUS * r->M + instance,
 				sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) break;
@@ -1114,8 +1195,10 @@ int runSingle(simcu_ *r, bool opOnly, double tstep, double tstop, double tmax, i
 	}
 	r->rawMaxPoints = saveMax; r->rawFirst = saveFirst; r->rawCount = saveCount;
 	r->prepared = false;
-	if (rc != 0) return -1;
+	if (rc != 0) { r->single = -1; return -1; }
 	collectStats(r);
+	r->single = -1;
+	r->ran = false;       /* the batch outputs were not produced by this launch */
 	return variablesOf(r, variables, numVariables);
 }
 
@@ -1131,6 +1214,14 @@ int simcuPrepare(simcu_ *r, double tstep, double tstop, double tmax, char *probe
 int simcuUpload(simcu_ *r, void *stream)
 {
 	if (!r || !r->prepared) return fail("simcuUpload before simcuPrepare");
+	if (r->paramsChanged) {
+		/* new per-instance values: the pivot sequences are re-derived on pilots of
+		 * the new sweep (and the kernel rebuilt if they changed) */
+		std::vector<std::string> names = r->probeNames;
+		std::vector<char *> probes;
+		for (size_t i = 0; i < names.size(); i++) probes.push_back(&names[i][0]);
+		return prepare(r, r->ctl.tstep, r->ctl.tstop, r->ctl.tmax, probes.data(), (int)probes.size(), false);
+	}
 	std::string err;
 	if (!refreshParameters(r->nl, r->M, r->prog, err)) return fail("%s", err.c_str());
 	return uploadParameters(r, (cudaStream_t)stream);
@@ -1221,12 +1312,29 @@ int simcuFetchRaw(simcu_ *r, int instance, double *data[], int *numPoints, int *
 	return rc;
 }
 
+int simcuFetchRawBlock(simcu_ *r, double *out, int *numPoints)
+{
+	if (!r || !r->ran || !out || !numPoints) return -1;
+	if (r->rawMaxPoints <= 0 || r->rawCount < 1) return fail("no raw record was kept (raw_max_points)");
+	CU(cudaMemcpy(numPoints, r->dCI.as<int>() + (size_t)CI_NPTS * r->M + r->rawFirst,
+			(size_t)r->rawCount * sizeof(int), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(out, r->dOutRaw.p, (size_t)r->rawMaxPoints * (r->prog.N + 1) * r->rawCount * 8,
+			cudaMemcpyDeviceToHost));
+	return 0;
+}
+
 int simcuRunTransientBatch(simcu_ *r, double tstep, double tstop, double tmax, int restart,
 		char *probes[], int numProbes, double *data[], int *numGrid, int *status[],
 		simcuStats_ *stats)
 {
 	if (!r) return -1;
-	if (!restart && r->ran) return fail("continuing a finished batch (restart = 0) is not supported");
+	/* core/simulator.c:111,138-140: restart = 0 after a finished transient would
+	 * continue it from the state it ended in.  The batch engine keeps no
+	 * per-instance state between launches, so this is refused, not ignored;
+	 * restart = 0 on a simulator that has not run is a normal start (:111). */
+	if (!restart && r->ranTransient)
+		return fail("continuing a finished transient (restart = 0) is not supported: "
+				"per-instance state is not kept between launches");
 	if (prepare(r, tstep, tstop, tmax, probes, numProbes, false)) return -1;
 	if (runDevice(r, 0, false)) return -1;
 	const size_t n = (size_t)r->M * r->ngrid * numProbes;
@@ -1274,7 +1382,10 @@ int simcuRunOperatingPointBatch(simcu_ *r, char *probes[], int numProbes, double
 int simcuRunTransient(simcu_ *r, double tstep, double tstop, double tmax, int restart,
 		int instance, double *data[], char **variables[], int *numPoints, int *numVariables)
 {
-	(void)restart;
+	if (!r) return -1;
+	if (!restart && r->ranTransient)      /* see simcuRunTransientBatch */
+		return fail("continuing a finished transient (restart = 0) is not supported: "
+				"per-instance state is not kept between launches");
 	return runSingle(r, false, tstep, tstop, tmax, instance, data, variables, numPoints, numVariables);
 }
 
@@ -1350,8 +1461,9 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	}
 	const int tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
 	const std::vector<double> consts[2] = {p.constOP, p.constTran};
-	const std::string src = assembleSource(p, sched, active, consts, probeRows, r->measures, tpb,
-			r->minBlocks, r->ctl.gmin);
+	JitConfig cfg;
+	cfg.threadsPerBlock = tpb; cfg.minBlocks = r->minBlocks; cfg.gmin = r->ctl.gmin; cfg.replay = r->replay;
+	const std::string src = assembleSource(p, sched, active, consts, probeRows, r->measures, cfg);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;
 	std::string err;

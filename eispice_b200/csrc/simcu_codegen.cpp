@@ -558,9 +558,10 @@ void emitRows(Out &o, const char *name, const std::vector<int> &rows)
 
 }  /* namespace */
 
-std::string generatePrelude(const Program &p, int numProbes, int numMeasures, int threadsPerBlock,
-		int minBlocks, double gmin)
+std::string generatePrelude(const Program &p, int numProbes, int numMeasures, const JitConfig &cfg)
 {
+	const int threadsPerBlock = cfg.threadsPerBlock, minBlocks = cfg.minBlocks;
+	const double gmin = cfg.gmin;
 	Out o;
 	o.f("#define SIMCU_JIT 1\n");
 	o.f("#define SIMCU_N %d\n#define SIMCU_NNZ %d\n#define SIMCU_SD %d\n#define SIMCU_SI %d\n",
@@ -570,6 +571,7 @@ std::string generatePrelude(const Program &p, int numProbes, int numMeasures, in
 	o.f("#define SIMCU_NPROBES %d\n#define SIMCU_TPB %d\n#define SIMCU_MINB %d\n", numProbes,
 			threadsPerBlock, minBlocks > 0 ? minBlocks : 1);
 	o.f("#define SIMCU_NMEASURES %d\n", numMeasures);
+	o.f("#define SIMCU_REPLAY %d\n", cfg.replay ? 1 : 0);
 	o.f("#define HUGE_VAL (__longlong_as_double(0x7ff0000000000000LL))\n");
 	o.f("#define SIMCU_GMIN (%s)\n", lit(gmin).c_str());
 	o.f("#define M_PI 3.14159265358979323846\n");

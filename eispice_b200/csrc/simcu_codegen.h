@@ -12,9 +12,21 @@
 
 namespace simcu {
 
+/* compile-time choices of one specialised kernel besides the topology itself */
+struct JitConfig {
+	int threadsPerBlock = 64;
+	int minBlocks = 0;        /* __launch_bounds__ second argument (0 = 1) */
+	double gmin = 1e-15;      /* guard of every calculon division, folded into the code */
+	int replay = 0;           /* 1: replay an attempt log instead of own step control (tests) */
+	bool operator==(const JitConfig &o) const
+	{
+		return threadsPerBlock == o.threadsPerBlock && minBlocks == o.minBlocks && gmin == o.gmin &&
+			replay == o.replay;
+	}
+};
+
 /* #defines of the topology's sizes; first part of the translation unit */
-std::string generatePrelude(const Program &p, int numProbes, int numMeasures, int threadsPerBlock,
-		int minBlocks, double gmin);
+std::string generatePrelude(const Program &p, int numProbes, int numMeasures, const JitConfig &cfg);
 /* device records, expressions and the unrolled LU of both phases */
 std::string generateTopology(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
@@ -23,7 +35,7 @@ std::string generateTopology(const Program &p, const Schedule sched[2],
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
 		const std::vector<int> &probeRows, const std::vector<int> &measures,
-		int threadsPerBlock, int minBlocks, double gmin);
+		const JitConfig &cfg);
 
 /* A compiled kernel.  compile() needs no GPU (NVRTC only); load() does. */
 struct JitKernel {

@@ -79,10 +79,9 @@ void jitSetNvrtcPath(const char *path) { gNvrtcHint = path ? path : ""; }
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
 		const std::vector<int> &probeRows, const std::vector<int> &measures,
-		int threadsPerBlock, int minBlocks, double gmin)
+		const JitConfig &cfg)
 {
-	std::string s = generatePrelude(p, (int)probeRows.size(), (int)measures.size() / 2,
-			threadsPerBlock, minBlocks, gmin);
+	std::string s = generatePrelude(p, (int)probeRows.size(), (int)measures.size() / 2, cfg);
 	s += kSrcProgram;
 	s += kSrcCalc;
 	s += kSrcDevice;

@@ -92,7 +92,7 @@ enum {
 enum {
 	CI_ORDER = 0, CI_STATUS, CI_DONE, CI_ACCEPTED, CI_REJ_LTE, CI_REJ_NC,
 	CI_NFACT, CI_NFACT_OP, CI_NPTS, CI_HCOUNT, CI_GRIDIDX, CI_ATTEMPTS,
-	CI_BREAK, CI_NUM
+	CI_BREAK, CI_REPLAY_DIFF, CI_NUM
 };
 
 /* options of the loop: reference include/control.h:34-56 */
@@ -152,6 +152,12 @@ typedef struct {
 	int lanes;                /* active lanes per warp (power of two <= 32) */
 	const int *order;         /* processing order of the instances (NULL = as given) */
 	int count;                /* instances this launch processes (<= M; M stays the stride) */
+	int claimBelow;           /* an idle lane claims once <= this many lanes of its warp are busy */
+	/* replay of an attempt log (test instrumentation): entries
+	 * [replayOff[i], replayOff[i+1]) of instance i; flag = order | outcome << 4 | solves << 8 */
+	const int *replayOff;
+	const double *replayTime;
+	const int *replayFlag;
 } SimcuArgs;
 
 #endif

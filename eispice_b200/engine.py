@@ -41,7 +41,7 @@ class Stats(C.Structure):
                 ("jitCompiles", C.c_int), ("registersPerThread", C.c_int),
                 ("localBytesPerThread", C.c_int), ("gridBlocks", C.c_int),
                 ("lanesPerWarp", C.c_int), ("pivotBreakdowns", C.c_longlong),
-                ("historyRetries", C.c_int)]
+                ("historyRetries", C.c_int), ("replayDiffs", C.c_longlong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -81,6 +81,7 @@ def lib():
     L.simcuSetInstanceTableSet.argtypes = [vp, cp, vp, C.c_int]
     L.simcuSetOption.argtypes = [vp, cp, C.c_double]
     L.simcuSetPivots.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+    L.simcuSetReplayLog.argtypes = [vp, vp, vp, vp]
     L.simcuRunTransient.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int,
                                     C.c_int, vp, vp, ip, ip]
     L.simcuRunOperatingPoint.argtypes = [vp, C.c_int, vp, vp, ip, ip]
@@ -96,6 +97,7 @@ def lib():
     L.simcuDeviceOutput.argtypes = [vp]
     L.simcuGetStats.argtypes = [vp, vp]
     L.simcuFetchRaw.argtypes = [vp, C.c_int, vp, ip, ip]
+    L.simcuFetchRawBlock.argtypes = [vp, vp, vp]
     L.simcuFetchCounters.argtypes = [vp, cp, vp]
     L.simcuSetMeasures.argtypes = [vp, vp, vp, vp, C.c_int]
     L.simcuFetchMeasures.argtypes = [vp, vp]
@@ -280,6 +282,24 @@ class Engine:
         pr = np.ascontiguousarray(pr, dtype=np.int32)
         self.L.simcuSetPivots(self.h, phase, pc.ctypes.data, pr.ctypes.data, len(pc))
 
+    def set_replay_log(self, logs):
+        """Test instrumentation: logs[i] = (times, flags) of instance i as the CPU
+        oracle recorded them (tests/backends.py: OracleSim.attempt_log); the run
+        then replays those attempts instead of its own step control."""
+        if logs is None:
+            self.L.simcuSetReplayLog(self.h, None, None, None)
+            self.set_option("replay", 0)
+            return
+        if len(logs) != self.num_instances:
+            raise ValueError("one attempt log per instance")
+        off = np.zeros(self.num_instances + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(t) for t, _ in logs])
+        times = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.float64) for t, _ in logs]))
+        flags = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.int32) for _, f in logs]))
+        if self.L.simcuSetReplayLog(self.h, off.ctypes.data, times.ctypes.data, flags.ctypes.data):
+            raise ValueError("bad replay log")
+        self.set_option("replay", 1)
+
     # -- introspection ----------------------------------------------------------
     def num_unknowns(self):
         return self.L.simcuNumUnknowns(self.h)
@@ -425,6 +445,19 @@ class Engine:
         self.L.simcuFree(data)
         return arr
 
+    def fetch_raw_all(self, max_points, count=None):
+        """Raw records of instances [0, count) kept by the last batch (options
+        raw_max_points = max_points, raw_count = count): list of [npts, N+1] arrays."""
+        count = self.num_instances if count is None else count
+        nv = self.num_unknowns() + 1
+        block = np.empty((max_points, nv, count), dtype=np.float64)
+        npts = np.empty(count, dtype=np.int32)
+        if self.L.simcuFetchRawBlock(self.h, block.ctypes.data, npts.ctypes.data):
+            raise RuntimeError("simcuFetchRawBlock failed")
+        if (npts > max_points).any():
+            raise RuntimeError("raw record overflow: %d points" % npts.max())
+        return [np.ascontiguousarray(block[:npts[i], :, i]) for i in range(count)]
+
     def tran_batch(self, tstep, tstop, tmax=0.0, params=None, probes=(), measures=None,
                    **options):
         for k, v in options.items():
@@ -433,8 +466,7 @@ class Engine:
             self.set_measures(measures)
         if params:
             self.set_params(params)
-        self.prepare(tstep, tstop, tmax, probes)
-        self.upload()
+        self.prepare(tstep, tstop, tmax, probes)     # includes the parameter upload
         self.run_device()
         data, status = self.fetch()
         res = BatchResult(data, output_grid(tstep, tstop, self.ngrid), status,

@@ -69,6 +69,7 @@ typedef struct {
 	int lanesPerWarp;          /* instances per warp of the specialised kernel */
 	long long pivotBreakdowns; /* transient attempts rejected for a zero pivot */
 	int historyRetries;        /* instances re-run with a deeper T-line history ring */
+	long long replayDiffs;     /* replay mode: attempts this engine would have decided otherwise */
 } simcuStats_;
 
 /* simulatorNew (simulator.h:33): r must be NULL */
@@ -135,7 +136,10 @@ int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
  * table set for processing), history_retry (1: re-run instances that
  * outran the T-line history ring, with a deeper ring and 32 x the attempts of
  * an average instance), interpreter (1: run the batch on the generic
- * table-driven kernels instead of the NVRTC-specialised one; for verification);
+ * table-driven kernels instead of the NVRTC-specialised one; for verification),
+ * claim_below (0..31: an idle lane of the specialised kernel claims its next
+ * instance once at most this many lanes of its warp are still busy; 31 = at
+ * once, 0 = whole warps start together), replay (see simcuSetReplayLog);
  * r = NULL: quiet (0/1) */
 int simcuSetOption(simcu_ *r, char *name, double value);
 /* Force the pivot sequence of a phase (0 = operating point, 1 = transient)
@@ -144,12 +148,25 @@ int simcuSetOption(simcu_ *r, char *name, double value);
  * feeds perm_c / perm_r of its own libs/superlu (dgssvx, core/matrix.c:82-118;
  * SURVEY.md appendix B).  pc = NULL returns to the built-in analysis. */
 int simcuSetPivots(simcu_ *r, int phase, const int *pc, const int *pr, int n);
+/* Test instrumentation (option replay = 1): instead of its own accept / reject
+ * decisions (core/simulator.c:186-214) instance i replays the attempts
+ * [offsets[i], offsets[i+1]) of a log: times[] = the time each attempt tried,
+ * flags[] = integration order | outcome << 4 | LU solves << 8, outcome 0
+ * accepted, 1 rejected by the LTE test, 2 rejected for non-convergence.  The
+ * log comes from the CPU oracle (oracle/eis_oracle.h: eoGetAttemptLog), so that
+ * both sides take identical steps and every unknown of every accepted step can
+ * be held to 1e-6 / 1e-9.  Copied immediately; offsets = NULL clears it. */
+int simcuSetReplayLog(simcu_ *r, const int *offsets, const double *times, const int *flags);
 
 /* ---- runs ----------------------------------------------------------------- */
 /* simulatorRunTransient (simulator.h:35-38) for ONE instance (index
  * `instance`), same result layout: *data is malloc'd [numPoints][numVariables]
  * row-major with column 0 = time, *variables is a malloc'd NULL-terminated
- * array (strings owned by the handle). Free both with simcuFree. */
+ * array (strings owned by the handle). Free both with simcuFree.
+ * restart: the reference continues a finished transient when restart = 0
+ * (core/simulator.c:111,138-140).  This engine keeps no per-instance state
+ * between launches: restart = 0 after a completed transient returns -1 with a
+ * message; on a handle that has not run a transient it is a normal start. */
 int simcuRunTransient(simcu_ *r, double tstep, double tstop, double tmax,
 		int restart, int instance, double *data[], char **variables[],
 		int *numPoints, int *numVariables);
@@ -200,14 +217,19 @@ int simcuGetStats(simcu_ *r, simcuStats_ *stats);
 int simcuSetMeasures(simcu_ *r, char *probes[], const int *kinds, const double *levels, int n);
 int simcuFetchMeasures(simcu_ *r, double *out);
 /* per-instance counters of the last batch into out[numInstances]; which is
- * status, accepted, rejected_lte, rejected_nc, factorizations or
- * op_factorizations */
+ * status, accepted, rejected_lte, rejected_nc, factorizations,
+ * op_factorizations, pivot_breakdowns or replay_diff */
 int simcuFetchCounters(simcu_ *r, char *which, int *out);
 /* raw (time, X) record of one instance of the last batch, reference layout
  * (core/matrix.c:430-470): malloc'd [numPoints][numVariables], column 0 = time.
  * Needs the options raw_max_points > 0 and raw_first / raw_count covering it. */
 int simcuFetchRaw(simcu_ *r, int instance, double *data[], int *numPoints,
 		int *numVariables);
+/* all raw records of the last batch in one copy: out is
+ * [raw_max_points][numVariables][raw_count] (instance fastest), numPoints
+ * [raw_count] the points each instance produced (may exceed raw_max_points:
+ * then its record is truncated) */
+int simcuFetchRawBlock(simcu_ *r, double *out, int *numPoints);
 
 /* ---- introspection (host only, no GPU needed) ----------------------------- */
 int simcuNumUnknowns(simcu_ *r);

@@ -37,5 +37,8 @@ for d in core devices math; do
 	done
 done
 cc gnu99 ref_shim "$HERE/ref_shim.c"
-gcc -shared -o "$OUT/libeispice_ref.so" $objs -lm
+# link-time probe of SuperLU's permutations (ref_probe.c): the reference's own
+# call of dgssvx is routed through it, no reference source is touched
+cc gnu99 ref_probe "$HERE/ref_probe.c"
+gcc -shared -Wl,--wrap=dgssvx -o "$OUT/libeispice_ref.so" $objs -lm
 echo "build_ref: wrote $OUT/libeispice_ref.so"

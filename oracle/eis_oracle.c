@@ -992,6 +992,9 @@ struct eo_sim {
 	int *fixPc[2], *fixPr[2];
 	int phase;
 	eo_stats st;
+	/* attempt log (tests only): one entry per transient attempt, in order */
+	int logOn, logN, logCap;
+	double *logTime; int *logFlag;
 };
 
 /* --- rows & pattern: core/row.c:46-66,163-204, core/matrix.c:292-346 ------ */
@@ -1109,6 +1112,7 @@ void eoDestroy(eo_sim *s)
 	free(s->rdone); free(s->cdone); free(s->prow); free(s->pcol); free(s->pinv);
 	free(s->htime); free(s->hX);
 	for (i = 0; i < 2; i++) { free(s->fixPc[i]); free(s->fixPr[i]); }
+	free(s->logTime); free(s->logFlag);
 	free(s);
 }
 void eoFree(void *p) { free(p); }
@@ -1944,17 +1948,47 @@ int eoRunOperatingPoint(eo_sim *s, double **data, char ***variables,
 	return matGetSolution(s, data, variables, numPoints, numVariables);
 }
 
+/* The attempt log: what core/simulator.c:156-218 decided for every attempt of
+ * the last transient - the time it tried, the integration order it used (after
+ * the break-point reset, :172), how many LU solves its Newton loop took and
+ * whether it was accepted (0), rejected by the LTE test (1, :191-198) or for
+ * non-convergence (2, :201-214).  The GPU engine replays it (option "replay")
+ * so that both sides take the same steps and can be compared value by value. */
+static void logAttempt(eo_sim *s, double time, int order, int outcome, int solves)
+{
+	if (!s->logOn) return;
+	if (s->logN == s->logCap) {
+		s->logCap = s->logCap ? 2 * s->logCap : 4096;
+		s->logTime = realloc(s->logTime, sizeof(double) * s->logCap);
+		s->logFlag = realloc(s->logFlag, sizeof(int) * s->logCap);
+	}
+	s->logTime[s->logN] = time;
+	s->logFlag[s->logN] = EO_LOG_FLAG(order, outcome, solves);
+	s->logN++;
+}
+
+void eoSetAttemptLog(eo_sim *s, int on) { s->logOn = on; s->logN = 0; }
+
+int eoGetAttemptLog(eo_sim *s, const double **times, const int **flags)
+{
+	if (times) *times = s->logTime;
+	if (flags) *flags = s->logFlag;
+	return s->logN;
+}
+
 int eoRunTransient(eo_sim *s, double tstep, double tstop, double tmax,
 		int restart, double **data, char ***variables, int *numPoints,
 		int *numVariables)
 {
 	Control *c;
-	int linCount = 0, breakPoint = 0, i;
+	int linCount = 0, breakPoint = 0, i, usedOrder;
+	long solves0;
 	double maxStep, thisStep = 0.0, lteStep = 0.0, prevTime = 0.0, oldMinstep;
 
 	if (s == NULL) return -1;
 	c = &s->ctl;
 	memset(&s->st, 0, sizeof s->st);
+	s->logN = 0;
 
 	if (tmax == 0.0) {                          /* :91-94 */
 		tmax = tstop / 50;
@@ -1994,6 +2028,8 @@ int eoRunTransient(eo_sim *s, double tstep, double tstop, double tmax,
 				breakPoint = breakPoint || loc;
 			}
 			if (breakPoint) c->integratorOrder = 1;
+			usedOrder = c->integratorOrder;
+			solves0 = s->st.factorizations;
 			for (i = 0; i < s->ndev; i++) TRY(devIntegrate(s, s->dev[i]));
 			linCount = simSolve(s, c->itl4);    /* :182 */
 			if (linCount < 0) return -1;
@@ -2005,13 +2041,18 @@ int eoRunTransient(eo_sim *s, double tstep, double tstop, double tmax,
 					if (has && (loc > 0.0) && (loc < lteStep)) lteStep = loc;
 				}
 				if (lteStep < (0.9 * thisStep)) {
+					logAttempt(s, c->time, usedOrder, 1, (int)(s->st.factorizations - solves0));
 					if (lteStep < (tstep * 1e-9))
 						FAIL("Timestep %es is too Small at %es", lteStep, c->time);
 					c->integratorOrder = 1;
 					thisStep = lteStep;
 					s->st.rejected_lte++;
-				} else break;
+				} else {
+					logAttempt(s, c->time, usedOrder, 0, (int)(s->st.factorizations - solves0));
+					break;
+				}
 			} else {                            /* :201-214 */
+				logAttempt(s, c->time, usedOrder, 2, (int)(s->st.factorizations - solves0));
 				thisStep = thisStep / 8;
 				if (thisStep < (tstep * 1e-9))
 					FAIL("Timestep %es is too Small at %es", thisStep, c->time);

@@ -67,6 +67,14 @@ int eoSetParam(eo_sim *s, const char *refdes, const char *name, double v);
  * phase 0 = operating point, 1 = transient. */
 int eoSetPivots(eo_sim *s, int phase, const int *pc, const int *pr, int n);
 
+/* Attempt log of the last transient (test instrumentation, see eis_oracle.c):
+ * one entry per attempt in order - the time tried and a flag word
+ * order | outcome << 4 | solves << 8, outcome 0 accepted / 1 LTE reject /
+ * 2 non-convergence.  The arrays stay owned by the simulator. */
+#define EO_LOG_FLAG(order, outcome, solves) ((order) | ((outcome) << 4) | ((solves) << 8))
+void eoSetAttemptLog(eo_sim *s, int on);
+int eoGetAttemptLog(eo_sim *s, const double **times, const int **flags);
+
 int eoRunTransient(eo_sim *s, double tstep, double tstop, double tmax,
 		int restart, double **data, char ***variables, int *numPoints,
 		int *numVariables);

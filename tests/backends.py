@@ -73,6 +73,8 @@ def oracle_lib():
         lib.eoGetStats.argtypes = [C.c_void_p, C.c_void_p]
         lib.eoCalcEval.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_double, C.c_void_p, C.c_void_p]
+        lib.eoSetAttemptLog.argtypes = [C.c_void_p, C.c_int]
+        lib.eoGetAttemptLog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _oracle = lib
     return _oracle
 
@@ -108,6 +110,9 @@ def ref_lib():
         lib.ref_shim_quiet.argtypes = [C.c_int]
         lib.ref_calc_eval.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_double, C.c_void_p, C.c_void_p]
+        lib.ref_probe_capture.argtypes = [C.c_int]
+        lib.ref_probe_count.argtypes = [C.c_void_p]
+        lib.ref_probe_sequence.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         _ref = lib
     return _ref
 
@@ -201,6 +206,20 @@ class OracleSim:
         rc = self.lib.eoRunOperatingPoint(self.h, C.byref(data), C.byref(names),
                                           C.byref(npts), C.byref(nvar))
         return self._collect(rc, data, names, npts, nvar)
+
+    def log_attempts(self, on=True):
+        """Record (time, order, outcome, solves) of every transient attempt."""
+        self.lib.eoSetAttemptLog(self.h, 1 if on else 0)
+
+    def attempt_log(self):
+        """(times[n], flags[n]) of the last transient; flags = order |
+        outcome << 4 | solves << 8, outcome 0 accepted / 1 LTE / 2 non-convergence."""
+        t, f = _dp(), C.POINTER(C.c_int)()
+        n = self.lib.eoGetAttemptLog(self.h, C.byref(t), C.byref(f))
+        if n == 0:
+            return np.zeros(0), np.zeros(0, dtype=np.int32)
+        return (np.ctypeslib.as_array(t, shape=(n,)).copy(),
+                np.ctypeslib.as_array(f, shape=(n,)).copy())
 
     def stats(self):
         st = EoStats()
@@ -327,6 +346,27 @@ class RefSim:
         rc = self.lib.simulatorRunOperatingPoint(self.h, C.byref(data), C.byref(names),
                                                  C.byref(npts), C.byref(nvar))
         return self._collect(rc, data, names, npts, nvar)
+
+
+def superlu_sequences(netlist, vi_set, tstep, tstop, max_records=100000):
+    """Run one instance on the unmodified reference and return the pivot
+    sequences of every full factorisation SuperLU did (oracle/ref_probe.c):
+    (pc[k][N], pr[k][N]); k = 0 is the operating point, k = 1 the first
+    transient attempt."""
+    lib = ref_lib()
+    sim = RefSim(netlist, vi_set)
+    lib.ref_probe_capture(max_records)
+    try:
+        sim.tran(tstep, tstop)
+    finally:
+        n = C.c_int(0)
+        cnt = lib.ref_probe_count(C.byref(n))
+        lib.ref_probe_capture(0)
+    pc = np.zeros((cnt, n.value), dtype=np.int32)
+    pr = np.zeros((cnt, n.value), dtype=np.int32)
+    for k in range(cnt):
+        lib.ref_probe_sequence(k, pc[k].ctypes.data, pr[k].ctypes.data)
+    return pc, pr
 
 
 def eval_expr(lib_kind, expr, names, values, min_div=1e-15):
