@@ -113,6 +113,8 @@ struct _simcu {
 	JitConfig jitCfg;               /* what r->jit was compiled with */
 	int replay = 0;                 /* test instrumentation: replay an attempt log */
 	int claimBelow = 31;            /* lane claiming policy of the specialised kernel */
+	int blockSync = 0;              /* warps of a block run their attempts in step (I-cache sharing) */
+	double growthLimit = 1e6;       /* LU multiplier magnitude that counts as pivot growth */
 	std::vector<int> replayOff, replayFlag;
 	std::vector<double> replayTime;
 	std::vector<char> active[2];
@@ -534,6 +536,8 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "max_blocks_per_sm") r->maxBlocksPerSM = (int)value;
 	else if (n == "claim_below") r->claimBelow = std::max(0, std::min(31, (int)value));
 	else if (n == "replay") r->replay = (value != 0.0);
+	else if (n == "block_sync") r->blockSync = (value != 0.0);
+	else if (n == "growth_limit") r->growthLimit = value;
 	else return fail("unknown option %s", name);
 	r->prepared = false;
 	return 0;
@@ -774,7 +778,7 @@ int buildJitKernel(simcu_ *r)
 {
 	JitConfig cfg;
 	cfg.threadsPerBlock = r->tpb; cfg.minBlocks = r->minBlocksUsed; cfg.gmin = r->ctl.gmin;
-	cfg.replay = r->replay;
+	cfg.replay = r->replay; cfg.blockSync = r->blockSync; cfg.growthLimit = r->growthLimit;
 	if (r->jit && r->jitProbes == r->probeRows && r->jitCfg == cfg && r->jitMeasures == r->measures)
 		return 0;
 	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows,
@@ -954,7 +958,7 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		 * warps thrash L1 with their local-memory windows - so 32 unless asked) */
 		int pow2 = 1;
 		while (pow2 * 2 <= lanes) pow2 *= 2;
-		r->lanes = pow2;
+		r->lanes = r->blockSync ? 32 : pow2;      /* the block barrier needs every thread */
 		const long long warps = ((long long)M + r->lanes - 1) / r->lanes;
 		const long long want = (warps + wpb - 1) / wpb;
 		r->jitBlocks = (int)std::max(1LL, std::min(want, capacity / wpb));
@@ -1094,7 +1098,7 @@ int collectStats(simcu_ *r)
 	CU(cudaMemcpy(ci.data(), r->dCI.p, ci.size() * sizeof(int), cudaMemcpyDeviceToHost));
 	simcuStats_ &s = r->stats;
 	s.accepted = s.rejectedLTE = s.rejectedNC = s.factorizations = s.opFactorizations = s.failed = 0;
-	s.pivotBreakdowns = 0; s.replayDiffs = 0;
+	s.pivotBreakdowns = 0; s.replayDiffs = 0; s.growthWarnings = 0;
 	for (int i = 0; i < M; i++) {
 		if (r->single >= 0 && i != r->single) continue;
 		s.accepted += ci[(size_t)CI_ACCEPTED * M + i];
@@ -1106,6 +1110,7 @@ int collectStats(simcu_ *r)
 		if (!r->interpreter) {
 			s.pivotBreakdowns += ci[(size_t)CI_BREAK * M + i];
 			s.replayDiffs += ci[(size_t)CI_REPLAY_DIFF * M + i];
+			s.growthWarnings += ci[(size_t)CI_GROWTH * M + i];
 		}
 	}
 	const Program &p = r->prog;
@@ -1229,15 +1234,31 @@ int simcuUpload(simcu_ *r, void *stream)
 
 int simcuRunDevice(simcu_ *r, void *stream) { return runDevice(r, (cudaStream_t)stream, false); }
 
+int simcuTransposeOutput(simcu_ *r, void *stream, void **deviceData, void **deviceStatus,
+		int *numInstances, int *valuesPerInstance)
+{
+	if (!r || !r->ran) return fail("simcuTransposeOutput before simcuRunDevice");
+	cudaStream_t st = (cudaStream_t)stream;
+	const int M = r->M, rows = r->ngrid * (int)r->probeRows.size();
+	if (rows > 0) {
+		if (r->dOutT.reserve((size_t)rows * M * 8)) return -1;
+		if (simcuLaunchTranspose(r->dOutGrid.as<double>(), r->dOutT.as<double>(), M, rows, st))
+			return fail("transpose kernel launch failed");
+	}
+	if (deviceData) *deviceData = rows > 0 ? r->dOutT.p : nullptr;
+	if (deviceStatus) *deviceStatus = r->dCI.as<int>() + (size_t)CI_STATUS * M;
+	if (numInstances) *numInstances = M;
+	if (valuesPerInstance) *valuesPerInstance = rows;
+	return 0;
+}
+
 int simcuFetch(simcu_ *r, double *data, int *status, void *stream)
 {
 	if (!r || !r->ran) return fail("simcuFetch before simcuRunDevice");
 	cudaStream_t st = (cudaStream_t)stream;
 	const int M = r->M, rows = r->ngrid * (int)r->probeRows.size();
 	if (data && rows > 0) {
-		if (r->dOutT.reserve((size_t)rows * M * 8)) return -1;
-		if (simcuLaunchTranspose(r->dOutGrid.as<double>(), r->dOutT.as<double>(), M, rows, st))
-			return fail("transpose kernel launch failed");
+		if (simcuTransposeOutput(r, stream, nullptr, nullptr, nullptr, nullptr)) return -1;
 		CU(cudaMemcpyAsync(data, r->dOutT.p, (size_t)rows * M * 8, cudaMemcpyDeviceToHost, st));
 	}
 	if (status)
@@ -1293,7 +1314,7 @@ int simcuFetchCounters(simcu_ *r, char *which, int *out)
 	static const struct { const char *name; int row; } rows[] = {
 		{"status", CI_STATUS}, {"accepted", CI_ACCEPTED}, {"rejected_lte", CI_REJ_LTE},
 		{"rejected_nc", CI_REJ_NC}, {"factorizations", CI_NFACT}, {"op_factorizations", CI_NFACT_OP},
-		{"pivot_breakdowns", CI_BREAK}};
+		{"pivot_breakdowns", CI_BREAK}, {"replay_diff", CI_REPLAY_DIFF}, {"pivot_growth", CI_GROWTH}};
 	for (size_t i = 0; i < sizeof rows / sizeof rows[0]; i++)
 		if (!std::strcmp(which, rows[i].name)) {
 			CU(cudaMemcpy(out, r->dCI.as<int>() + (size_t)rows[i].row * r->M, (size_t)r->M * 4,

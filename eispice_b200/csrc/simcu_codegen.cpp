@@ -490,7 +490,7 @@ void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vec
 	const int N = p.N, F = s.F;
 	o.f("/* %s: %d unknowns, %d matrix slots (%d fill), %d L + %d U off-diagonal entries */\n",
 			phase ? "transient" : "operating point", N, F, F - p.nnzA, s.nL, s.nU);
-	o.f("DEV void genFactorSolve%d(Inst &c)\n{\n\tbool bad = false;\n", phase);
+	o.f("DEV void genFactorSolve%d(Inst &c)\n{\n\tbool bad = false, grow = false;\n", phase);
 	/* which slots the schedule touches */
 	std::vector<char> used(F, 0);
 	{
@@ -529,7 +529,9 @@ void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vec
 		o.f("\tconst double i%d = 1.0 / w%d; bad |= (w%d == 0.0) | !isfinite(i%d);\n", k, d, d, k);
 		for (int r = 0; r < nL; r++) {
 			const int *e = lrow + r * (2 + nU);
-			o.f("\t{ const double l = w%d * i%d;", e[0], k);
+			/* growth guard: the fixed sequence was chosen on pilot instances; a
+			 * multiplier this large means the pivot has lost that many digits */
+			o.f("\t{ const double l = w%d * i%d; grow |= (fabs(l) > SIMCU_LMAX);", e[0], k);
 			for (int j = 0; j < nU; j++) o.f(" w%d -= l * w%d;", e[2 + j], u[2 * j]);
 			o.f(" y%d -= l * y%d; }\n", e[1] - F, yk);
 		}
@@ -546,7 +548,7 @@ void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vec
 		o.f(" y%d = acc * i%d; }\n", yk, k);
 	}
 	for (int col = 0; col < N; col++) o.f("\tc.Xv[%d] = y%d;\n", col, s.xslot[col] - F);
-	o.f("\tif (bad) c.err = SIMCU_ERR_SINGULAR;\n}\n\n");
+	o.f("\tif (bad) c.err = SIMCU_ERR_SINGULAR;\n\tif (grow) c.growth++;\n}\n\n");
 }
 
 void emitRows(Out &o, const char *name, const std::vector<int> &rows)
@@ -572,8 +574,10 @@ std::string generatePrelude(const Program &p, int numProbes, int numMeasures, co
 			threadsPerBlock, minBlocks > 0 ? minBlocks : 1);
 	o.f("#define SIMCU_NMEASURES %d\n", numMeasures);
 	o.f("#define SIMCU_REPLAY %d\n", cfg.replay ? 1 : 0);
+	o.f("#define SIMCU_BLOCKSYNC %d\n", cfg.blockSync ? 1 : 0);
 	o.f("#define HUGE_VAL (__longlong_as_double(0x7ff0000000000000LL))\n");
 	o.f("#define SIMCU_GMIN (%s)\n", lit(gmin).c_str());
+	o.f("#define SIMCU_LMAX (%s)\n", lit(cfg.growthLimit).c_str());
 	o.f("#define M_PI 3.14159265358979323846\n");
 	o.f("enum { SIMCU_OK = %d, SIMCU_ERR_TIMESTEP = %d, SIMCU_ERR_SINGULAR = %d, SIMCU_ERR_NAN = %d,\n"
 			"\tSIMCU_ERR_OP = %d, SIMCU_ERR_HISTORY = %d, SIMCU_ERR_BUDGET = %d };\n\n",

@@ -18,10 +18,12 @@ struct JitConfig {
 	int minBlocks = 0;        /* __launch_bounds__ second argument (0 = 1) */
 	double gmin = 1e-15;      /* guard of every calculon division, folded into the code */
 	int replay = 0;           /* 1: replay an attempt log instead of own step control (tests) */
+	int blockSync = 0;        /* 1: the warps of a block start every attempt together */
+	double growthLimit = 1e6; /* LU multipliers above this are counted (pivot growth guard) */
 	bool operator==(const JitConfig &o) const
 	{
 		return threadsPerBlock == o.threadsPerBlock && minBlocks == o.minBlocks && gmin == o.gmin &&
-			replay == o.replay;
+			replay == o.replay && blockSync == o.blockSync && growthLimit == o.growthLimit;
 	}
 };
 

@@ -62,6 +62,7 @@ struct Inst {
 	double time;
 	int order;
 	int err;             /* SIMCU_ERR_* of this instance (0 = ok) */
+	int growth;          /* factorisations with an LU multiplier above SIMCU_LMAX */
 	mutable double Av[SIMCU_DIM(SIMCU_NNZ)], Bv[SIMCU_DIM(SIMCU_N)];
 	mutable double Xv[SIMCU_DIM(SIMCU_N)], Xa[SIMCU_DIM(SIMCU_N)];
 	mutable double sv[SIMCU_DIM(SIMCU_SD)];
@@ -242,10 +243,46 @@ DEV double pwGetNextX(const Table &t, int &index, double x0)
  * time point, 1 = the one before, ...) instead of by ring position n % 3, so
  * every access has a compile-time index and the state can live in registers;
  * advancing the ring counter becomes a rotation.  Same values, same tests. */
+/* The reference compares theta = atan2(dx, dt) of this time point with the one
+ * of the previous point (checkbreak.c:57-66).  In raw SI units dt ~ 1e-11, so
+ * |theta| is within 1e-3 of pi/2 for any signal that moves, and exactly 0 for
+ * one that does not: > 97 % of the calls on the IBIS circuits.  The specialised
+ * kernel therefore keeps the ARGUMENTS (dx, dt) of both angles instead of the
+ * angles and decides from certified bounds - small: |dx| <= dt/2, |theta| <=
+ * 0.4637; big: |dx| >= 1000 dt, |theta| >= pi/2 - 0.001 - whenever they settle
+ * the comparison with pi/3 (margins >= 0.05 rad); otherwise from single-precision
+ * angles if those are more than 1e-3 away from the threshold, and only then from
+ * the two double-precision atan2 of the reference.  The decision is the
+ * reference's in every case; its cost is a handful of compares. */
+DEV int cbAngleBreak(double dy0, double dx0, double dy1, double dx1, double maxAngle)
+{
+	if (maxAngle > 0.93 && maxAngle < 1.10) {
+		const double a0 = fabs(dy0), a1 = fabs(dy1);
+		const bool f0 = (dx0 > 0.0) && (dx0 < HUGE_VAL), f1 = (dx1 > 0.0) && (dx1 < HUGE_VAL);
+		const bool s0 = f0 && (a0 <= 0.5 * dx0), s1 = f1 && (a1 <= 0.5 * dx1);
+		const bool b0 = f0 && (a0 >= 1000.0 * dx0) && (a0 < HUGE_VAL);
+		const bool b1 = f1 && (a1 >= 1000.0 * dx1) && (a1 < HUGE_VAL);
+		if (s0 && s1) return 0;
+		if (b0 && b1) return ((dy0 > 0.0) != (dy1 > 0.0)) ? 1 : 0;
+		if ((s0 && b1) || (b0 && s1)) return 1;
+		if (dx0 > 1e-30 && dx1 > 1e-30 && a0 < 1e30 && a1 < 1e30 && dx0 < 1e30 && dx1 < 1e30) {
+			const float d = fabsf(atan2f((float)dy0, (float)dx0) - atan2f((float)dy1, (float)dx1));
+			const float m = (float)maxAngle;
+			if (d > m + 1e-3f) return 1;
+			if (d < m - 1e-3f) return 0;
+		}
+	}
+	return (fabs(simcuAtan2(dy0, dx0) - simcuAtan2(dy1, dx1)) > maxAngle) ? 1 : 0;
+}
+
+/* state (9 doubles): x0 x1 dt0 | t0 t1 dt1 | dx0 dx1 - ; 0 = the slot of the
+ * current time point, 1 = the one before (the reference's third ring slot is
+ * never read) */
 DEV void cbInitialize(const Inst &c, int sb, int ib, double ic)
 {
-	SIMCU_UNROLL
-	for (int k = 0; k < 3; k++) { c.S(sb + k) = ic; c.S(sb + 3 + k) = 0.0; }
+	c.S(sb) = ic; c.S(sb + 1) = ic; c.S(sb + 2) = 0.0;
+	c.S(sb + 3) = 0.0; c.S(sb + 4) = 0.0; c.S(sb + 5) = 0.0;
+	c.S(sb + 6) = 0.0; c.S(sb + 7) = 0.0;
 	c.IS(ib) = 0;
 }
 
@@ -254,19 +291,20 @@ DEV int cbIsBreak(const Inst &c, int sb, int ib, double x, double maxAngle)
 	int n = c.IS(ib);
 	if (c.time > c.S(sb + 3)) {
 		n++; c.IS(ib) = n;
-		c.S(sb + 2) = c.S(sb + 1); c.S(sb + 1) = c.S(sb);               /* x */
-		c.S(sb + 5) = c.S(sb + 4); c.S(sb + 4) = c.S(sb + 3);           /* t */
-		c.S(sb + 8) = c.S(sb + 7); c.S(sb + 7) = c.S(sb + 6);           /* theta */
+		c.S(sb + 1) = c.S(sb);               /* x */
+		c.S(sb + 4) = c.S(sb + 3);           /* t */
+		c.S(sb + 7) = c.S(sb + 6);           /* arguments of theta */
+		c.S(sb + 5) = c.S(sb + 2);
 	}
 	/* (n - 1) % 3 < 0 only while the counter is still 0: then p = slot 0 = k */
 	const bool prev = (n >= 1);
 	c.S(sb) = x;
 	c.S(sb + 3) = c.time;
 	const double xp = prev ? c.S(sb + 1) : x, tp = prev ? c.S(sb + 4) : c.time;
-	const double th = simcuAtan2(x - xp, c.time - tp);
-	c.S(sb + 6) = th;
-	const double thp = prev ? c.S(sb + 7) : th;
-	return (fabs(th - thp) > maxAngle) ? 1 : 0;
+	const double dy = x - xp, dt = c.time - tp;
+	c.S(sb + 6) = dy; c.S(sb + 2) = dt;
+	const double dyp = prev ? c.S(sb + 7) : dy, dtp = prev ? c.S(sb + 5) : dt;
+	return cbAngleBreak(dy, dt, dyp, dtp, maxAngle);
 }
 #else
 DEV void cbInitialize(const Inst &c, int sb, int ib, double ic)

@@ -29,6 +29,9 @@
 #ifndef SIMCU_REPLAY
 #define SIMCU_REPLAY 0
 #endif
+#ifndef SIMCU_BLOCKSYNC
+#define SIMCU_BLOCKSYNC 0
+#endif
 
 /* statistics and status of a finished (or failed) instance; the data of an
  * instance with status != 0 is NaN from the failure time on */
@@ -56,6 +59,7 @@ DEV void jitFinish(const SimcuArgs &a, Inst &c, const double *meas, int accepted
 	ci[(size_t)CI_NPTS * M] = c.npts;
 	ci[(size_t)CI_BREAK * M] = pivotBreaks;
 	ci[(size_t)CI_REPLAY_DIFF * M] = replayDiff;
+	ci[(size_t)CI_GROWTH * M] = c.growth;
 }
 
 extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKernel(const SimcuArgs a, int opOnly)
@@ -89,6 +93,14 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 #endif
 
 	for (;;) {
+#if SIMCU_BLOCKSYNC
+		/* The warps of a block start every trip together, so they walk the same
+		 * code at about the same time and share its instruction-cache lines (the
+		 * loop body is several times the 32 KB L1.5 I-cache; unsynchronised, every
+		 * warp streams it from L2 on its own).  A warp's trip already waits for
+		 * its slowest lane, so waiting for the slowest warp costs little. */
+		if (!__syncthreads_or((busy || !exhausted) ? 1 : 0)) break;
+#endif
 		/* ---- claim: an idle lane takes the next instance of the queue once
 		 * few enough lanes of its warp are still busy (claimBelow = 31: at once;
 		 * 0: the whole warp starts its next 32 instances together).  The ballots
@@ -102,6 +114,7 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 				 * lanes of a warp follow similar waveforms and diverge less */
 				const int inst = a.order ? __ldg(&a.order[q]) : q;
 				c.i = inst; c.hcount = 0; c.npts = 0; c.gridIdx = 0; c.time = 0.0; c.order = 1; c.err = 0;
+				c.growth = 0;
 				/* parameters of this instance: broadcast constants or its own column */
 				SIMCU_UNROLL
 				for (int p = 0; p < SIMCU_NPARAM; p++) {
@@ -139,7 +152,9 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 			}
 		}
 		busyMask = __ballot_sync(lanesMask, busy);
+#if !SIMCU_BLOCKSYNC
 		if (busyMask == 0) break;      /* every lane is idle and the queue is empty */
+#endif
 		if (!busy) continue;
 
 		bool done = (c.err != 0);    /* instance over (finished or failed) */

@@ -92,7 +92,7 @@ enum {
 enum {
 	CI_ORDER = 0, CI_STATUS, CI_DONE, CI_ACCEPTED, CI_REJ_LTE, CI_REJ_NC,
 	CI_NFACT, CI_NFACT_OP, CI_NPTS, CI_HCOUNT, CI_GRIDIDX, CI_ATTEMPTS,
-	CI_BREAK, CI_REPLAY_DIFF, CI_NUM
+	CI_BREAK, CI_REPLAY_DIFF, CI_GROWTH, CI_NUM
 };
 
 /* options of the loop: reference include/control.h:34-56 */

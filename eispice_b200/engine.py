@@ -41,7 +41,17 @@ class Stats(C.Structure):
                 ("jitCompiles", C.c_int), ("registersPerThread", C.c_int),
                 ("localBytesPerThread", C.c_int), ("gridBlocks", C.c_int),
                 ("lanesPerWarp", C.c_int), ("pivotBreakdowns", C.c_longlong),
-                ("historyRetries", C.c_int), ("replayDiffs", C.c_longlong)]
+                ("historyRetries", C.c_int), ("replayDiffs", C.c_longlong),
+                ("growthWarnings", C.c_longlong)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class GatherStats(C.Structure):
+    """simcuGatherStats_ (include/simulator_cuda.h)"""
+    _fields_ = [("ncclMs", C.c_double), ("copyMs", C.c_double),
+                ("ncclBytes", C.c_longlong), ("copyBytes", C.c_longlong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -112,6 +122,11 @@ def lib():
     L.simcuFree.argtypes = [vp]
     L.simcuCompileOnly.argtypes = [vp, vp, C.c_int, vp, ip]
     L.simcuSetDevice.argtypes = [C.c_int]
+    L.simcuTransposeOutput.argtypes = [vp, vp, vp, vp, ip, ip]
+    L.simcuCommUniqueId.argtypes = [vp, C.c_int]
+    L.simcuCommInit.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
+    L.simcuCommDestroy.argtypes = [vp]
+    L.simcuGatherOutput.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -70,6 +70,9 @@ typedef struct {
 	long long pivotBreakdowns; /* transient attempts rejected for a zero pivot */
 	int historyRetries;        /* instances re-run with a deeper T-line history ring */
 	long long replayDiffs;     /* replay mode: attempts this engine would have decided otherwise */
+	long long growthWarnings;  /* factorisations whose largest LU multiplier exceeded growth_limit:
+	                            * the fixed pivot sequence (chosen on pilot instances) lost that many
+	                            * digits on this instance; per instance: counter "pivot_growth" */
 } simcuStats_;
 
 /* simulatorNew (simulator.h:33): r must be NULL */
@@ -139,7 +142,10 @@ int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
  * table-driven kernels instead of the NVRTC-specialised one; for verification),
  * claim_below (0..31: an idle lane of the specialised kernel claims its next
  * instance once at most this many lanes of its warp are still busy; 31 = at
- * once, 0 = whole warps start together), replay (see simcuSetReplayLog);
+ * once, 0 = whole warps start together), block_sync (1: the warps of a block
+ * start every attempt together and share instruction-cache lines),
+ * growth_limit (LU multiplier magnitude counted as pivot growth, default 1e6),
+ * replay (see simcuSetReplayLog);
  * r = NULL: quiet (0/1) */
 int simcuSetOption(simcu_ *r, char *name, double value);
 /* Force the pivot sequence of a phase (0 = operating point, 1 = transient)
@@ -207,6 +213,41 @@ int simcuNumGrid(simcu_ *r);
 /* device pointer of the gridded output, layout [numGrid][numProbes][M] */
 void *simcuDeviceOutput(simcu_ *r);
 int simcuGetStats(simcu_ *r, simcuStats_ *stats);
+/* Transposes the gridded output of the last batch to the host layout
+ * [numInstances][numGrid][numProbes] ON THE DEVICE (no copy out) and returns
+ * device pointers to it and to the status array, for callers that move the
+ * data on themselves (the NCCL gather below).  Any output may be NULL. */
+int simcuTransposeOutput(simcu_ *r, void *stream, void **deviceData, void **deviceStatus,
+		int *numInstances, int *valuesPerInstance);
+
+/* ---- multi-GPU: the one collective ---------------------------
+ * One process per GPU; instances are independent, so nothing is exchanged
+ * while stepping.  A sweep of nranks * M instances is dealt out round-robin:
+ * global instance g runs on rank g % nranks as its local instance g / nranks
+ * (every rank holds the same mix of corners).  simcuGatherOutput moves the
+ * finished waveforms of all ranks to `root` over NCCL (grouped ncclSend /
+ * ncclRecv between device buffers, NVLink / NVSwitch) and copies them to the
+ * root's host buffers once, in global instance order:
+ *   hostData    root only: [nranks * M][numGrid][numProbes]
+ *   hostStatus  root only: [nranks * M]
+ * Every rank must hold the same M, grid and probes.  The communicator is
+ * bootstrapped by the caller: rank 0 calls simcuCommUniqueId and hands the 128
+ * bytes to the other ranks by any means (torch.distributed broadcast, a file);
+ * then every rank calls simcuCommInit on its own GPU. */
+typedef struct _simcuComm simcuComm_;
+typedef struct {
+	double ncclMs;             /* device time of the grouped send / recv */
+	double copyMs;             /* root: device -> host copies */
+	long long ncclBytes;       /* bytes this rank sent (root: received) over NCCL */
+	long long copyBytes;       /* bytes copied to the host (root) */
+} simcuGatherStats_;
+int simcuCommVersion(void);                       /* NCCL version code, -1 without NCCL */
+int simcuCommUniqueId(char *id, int bytes);       /* bytes >= 128 */
+int simcuCommInit(simcuComm_ **c, int nranks, int rank, const char *id, int bytes);
+int simcuCommDestroy(simcuComm_ **c);
+int simcuGatherOutput(simcu_ *r, simcuComm_ *c, int root, double *hostData, int *hostStatus,
+		void *stream, simcuGatherStats_ *stats);
+
 /* Device-side post-processing (eispice NOTES:40 "Add post-processors"): n
  * running measures, each on one unknown probes[i] ("v(node)" / "i(refdes)"),
  * kinds[i] = 0 minimum, 1 maximum, 2 final value, 3 / 4 time of the first
@@ -218,7 +259,7 @@ int simcuSetMeasures(simcu_ *r, char *probes[], const int *kinds, const double *
 int simcuFetchMeasures(simcu_ *r, double *out);
 /* per-instance counters of the last batch into out[numInstances]; which is
  * status, accepted, rejected_lte, rejected_nc, factorizations,
- * op_factorizations, pivot_breakdowns or replay_diff */
+ * op_factorizations, pivot_breakdowns, replay_diff or pivot_growth */
 int simcuFetchCounters(simcu_ *r, char *which, int *out);
 /* raw (time, X) record of one instance of the last batch, reference layout
  * (core/matrix.c:430-470): malloc'd [numPoints][numVariables], column 0 = time.

@@ -14,6 +14,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Without a CUDA device the gpu-marked tests are skipped, not failed (the
+    product itself still fails loudly without a GPU: tests/test_bench_contract.py)."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _build_oracle():
     import backends

@@ -22,7 +22,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("cfg2") and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("cfg5") and d["vs_baseline"] is None
+    assert d["config"]["instances_per_gpu"] == 131072 and d["ms_per_step"] > 0
 
 
 def test_gpu_arm_fails_loudly_without_a_gpu():

@@ -1,0 +1,149 @@
+"""Fixed-step parity (BASELINE.json north_star, SURVEY.md 8d "Parity checks"):
+the CUDA engine REPLAYS the attempt sequence of the CPU oracle - the time, the
+integration order and the accept / reject outcome of every attempt
+(core/simulator.c:156-218) - for 256 random instances of each of the five
+BASELINE configurations drawn from the FULL-SIZE sweep, and every unknown at
+every accepted step must satisfy |gpu - oracle| <= 1e-6 |oracle| + 1e-9.
+
+The oracle runs with the GPU's fixed pivot sequence (oracle/eis_oracle.h:
+eoSetPivots), so both sides do the same arithmetic in the same order; what
+remains is FMA contraction and CUDA's libm.  The GPU takes no step-control
+decision in this mode, but still evaluates its own and counts disagreements
+(`replay_diff`), which must stay rare.
+
+A second set of tests feeds SuperLU's own permutations (read out of the
+unmodified reference's dgssvx by oracle/ref_probe.c) through simcuSetPivots -
+the north_star "pattern that SuperLU's symbolic analysis fixes" - and holds the
+engine to the same gate, and to the reference's own outcome where the
+reference aborts.
+"""
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+import backends
+import parity
+import parity_workers as pw
+import workloads
+from eispice_b200 import engine
+
+pytestmark = pytest.mark.gpu
+
+NSAMPLE = 256
+CAP = {"cfg1": 4000, "cfg2": 8000, "cfg3": 4000, "cfg4": 20000, "cfg5": 48000}
+
+
+@pytest.fixture(scope="module")
+def pool():
+    p = mp.get_context("spawn").Pool(min(32, len(os.sched_getaffinity(0))))
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("GPU tests need a CUDA device (there is no CPU fallback)")
+    engine.set_device(0)
+
+
+def _sample(cfg, n=NSAMPLE, seed=99):
+    w = workloads.make(cfg)                  # the BASELINE size
+    pick = np.sort(np.random.default_rng(seed).choice(w.M, min(n, w.M), replace=False))
+    sub = {k: np.asarray(v)[pick] for k, v in w.params.items()}
+    return w, pick, sub
+
+
+def _tight(raw, ref):
+    """(worst ratio, samples, samples inside) of one instance; inf if shapes differ."""
+    if raw.shape != ref.shape:
+        return float("inf"), ref.size, 0
+    r = np.abs(raw - ref) / (parity.RTOL_TIGHT * np.abs(ref) + parity.ATOL_TIGHT)
+    return float(r.max()), r.size, int((r <= 1.0).sum())
+
+
+def _replay(cfg, w, pick, sub, piv, pool, forced):
+    """Oracle (pivots piv) -> attempt logs -> GPU replay.  Returns per-instance
+    (worst ratio or None when the oracle aborted), GPU status, replay diffs."""
+    n = len(pick)
+    logged = pool.map(pw.oracle_logged, [(cfg, w.M, int(i), piv) for i in pick])
+    logs = [(x[1], x[2]) if x is not None else (np.zeros(0), np.zeros(0, np.int32)) for x in logged]
+    eng = engine.Engine(w.cct.netlist(), n)
+    if forced:
+        eng.set_pivots(0, piv[0], piv[1])
+        eng.set_pivots(1, piv[2], piv[3])
+    eng.set_replay_log(logs)
+    res = eng.tran_batch(w.tstep, w.tstop, 0.0, sub, w.probes, raw_max_points=CAP[cfg], raw_count=n)
+    got = tuple(np.asarray(p) for p in eng.pivots(0) + eng.pivots(1))
+    assert all(np.array_equal(a, b) for a, b in zip(got, piv)), "GPU did not use the oracle's pivots"
+    raws = eng.fetch_raw_all(CAP[cfg])
+    diffs = eng.counters("replay_diff")
+    attempts = np.array([len(t) for t, _ in logs])
+    eng.close()
+    worst = [None if logged[j] is None else _tight(raws[j], logged[j][0]) for j in range(n)]
+    return worst, res.status, diffs, attempts, logged
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+def test_replay_of_the_oracle_step_sequence_is_tight(cfg, pool):
+    w, pick, sub = _sample(cfg)
+    n = len(pick)
+    # the GPU's own pivot sequences for this sample (pilot analysis)
+    eng = engine.Engine(w.cct.netlist(), n)
+    eng.set_params(sub)
+    eng.prepare(w.tstep, w.tstop, 0.0, w.probes)
+    piv = tuple(np.asarray(p) for p in eng.pivots(0) + eng.pivots(1))
+    eng.close()
+    worst, status, diffs, attempts, logged = _replay(cfg, w, pick, sub, piv, pool, forced=True)
+    ran = [j for j in range(n) if worst[j] is not None]
+    assert len(ran) >= 0.97 * n, "the oracle aborted on %d of %d instances" % (n - len(ran), n)
+    assert (status[ran] == 0).all(), "GPU failed instances the oracle completed: %s" % status[ran]
+    ratios = np.array([worst[j][0] for j in ran])
+    bad = [(int(pick[j]), worst[j][0]) for j in ran if not worst[j][0] <= 1.0]
+    samples = sum(worst[j][1] for j in ran)
+    inside = sum(worst[j][2] for j in ran)
+    print("%s: %d instances replayed, %d samples, worst ratio %.3g, %d outside; own-decision "
+          "disagreements %d in %d attempts"
+          % (cfg, len(ran), samples, ratios.max(), samples - inside, diffs[ran].sum(), attempts[ran].sum()))
+    # EVERY unknown at EVERY accepted step of EVERY sampled instance - no allowance
+    assert not bad, "outside 1e-6/1e-9: %s" % bad[:10]
+    # the engine's own step control agrees with the oracle's on (nearly) every attempt
+    assert diffs[ran].sum() <= 2e-3 * attempts[ran].sum()
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+def test_superlu_permutations_through_set_pivots(cfg, pool):
+    """perm_c / perm_r of the reference's own SuperLU (operating point and first
+    transient factorisation of a typical instance) fed through simcuSetPivots:
+    instances the reference completes replay tight against the oracle under the
+    same sequence; instances the reference aborts on under ITS pivot order
+    (cfg5: every typ/falling corner - "Timestep too small" at 1.1e-13 s) are
+    flagged by the engine as well when it runs adaptively with that sequence."""
+    if not backends.ref_available():
+        pytest.skip("oracle/_ref not built")
+    w, pick, sub = _sample(cfg, 64, seed=5)
+    n = len(pick)
+    nl, s = w.instance_netlist(int(pick[0]))
+    pc, pr = backends.superlu_sequences(nl, s, w.tstep, w.tstop, max_records=4)
+    assert len(pc) >= 2
+    piv = (pc[0], pr[0], pc[1], pr[1])
+    worst, status, diffs, attempts, logged = _replay(cfg, w, pick, sub, piv, pool, forced=True)
+    ran = [j for j in range(n) if worst[j] is not None]
+    aborted = [j for j in range(n) if worst[j] is None]
+    assert len(ran) >= n // 2
+    bad = [(int(pick[j]), worst[j][0]) for j in ran if not worst[j][0] <= 1.0]
+    assert not bad, "outside 1e-6/1e-9 under SuperLU's sequence: %s" % bad[:10]
+    # adaptive run under the same sequence: what the oracle aborts, the engine flags
+    eng = engine.Engine(w.cct.netlist(), n)
+    eng.set_pivots(0, piv[0], piv[1])
+    eng.set_pivots(1, piv[2], piv[3])
+    res = eng.tran_batch(w.tstep, w.tstop, 0.0, sub, w.probes)
+    eng.close()
+    assert (res.status[ran] == 0).mean() >= 0.95
+    if aborted:
+        assert (res.status[aborted] != 0).mean() >= 0.9, (res.status[aborted], aborted)
+    print("%s under SuperLU's sequence: %d replayed tight, %d aborted by oracle and reference order"
+          % (cfg, len(ran), len(aborted)))

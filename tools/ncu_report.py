@@ -59,10 +59,17 @@ if len(rows) > 3 and rows[0][0] == "File Path":
     lines = [r for r in rows[3:] if r and r[0] not in ("",)]
     tot = sum(num(r[S]) for r in lines)
     toti = sum(num(r[I]) for r in lines)
-    try:
-        src = open(path).read().splitlines()
-    except OSError:
-        src = open(path.replace("/root/repo/", "")).read().splitlines()
+    import os
+    cands = [path, path.replace("/root/repo/", ""),
+             os.path.join("gpurun_out", "src", os.path.basename(path)),
+             os.path.join("profiles", "src", os.path.basename(path))]
+    src = None
+    for cnd in cands:
+        if os.path.exists(cnd):
+            src = open(cnd).read().splitlines()
+            break
+    if src is None:
+        raise SystemExit("source %s not found (run with SIMCU_JIT_DUMP=gpurun_out/src)" % path)
     func_at, cur = [], "?"
     for ln in src:
         m = re.match(r'^(?:DEV|DEVFN|SIMCU_HD|extern "C" __global__)\s+.*?(\w+)\(', ln)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One batched transient of a workload, for ncu: prepare, one warm-up run, one
-profiled run.  Usage: profile_run.py <cfg> <instances> [min_blocks_per_sm]"""
+profiled run.  Usage: profile_run.py <cfg> <instances> ["opt=val,opt=val"]"""
 import os
 import sys
 
@@ -12,8 +12,9 @@ from eispice_b200 import engine  # noqa: E402
 name, M = sys.argv[1], int(sys.argv[2])
 w = workloads.make(name, M)
 eng = engine.Engine(w.cct.netlist(), w.M)
-if len(sys.argv) > 3:
-    eng.set_option("min_blocks_per_sm", int(sys.argv[3]))
+for kv in [x for x in (sys.argv[3] if len(sys.argv) > 3 else "").split(",") if x]:
+    k, v = kv.split("=")
+    eng.set_option(k, float(v))
 eng.set_params(w.params)
 eng.prepare(w.tstep, w.tstop, 0.0, w.probes)
 eng.upload()
