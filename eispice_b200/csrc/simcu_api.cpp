@@ -113,9 +113,11 @@ struct _simcu {
 	JitConfig jitCfg;               /* what r->jit was compiled with */
 	int replay = 0;                 /* test instrumentation: replay an attempt log */
 	int claimBelow = 31;            /* lane claiming policy of the specialised kernel */
-	int blockSync = 0;              /* warps of a block run their attempts in step (I-cache sharing) */
+	int blockSync = -1;             /* warps of a block run their attempts in step (I-cache sharing); -1 = automatic */
+	int blockSyncUsed = 0;
 	double growthLimit = 1e6;       /* LU multiplier magnitude that counts as pivot growth */
-	std::vector<int> replayOff, replayFlag;
+	int tlinePrefetch = 1;          /* locate + prefetch pass over the T-lines (>= 2 lines) */
+	std::vector<int> replayOff, replayFlag, replayLinOff, replayLin;
 	std::vector<double> replayTime;
 	std::vector<char> active[2];
 	std::vector<double> consts[2];      /* per phase: literal value of a slot, NaN = varies */
@@ -132,7 +134,7 @@ struct _simcu {
 	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
 		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
 		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2, dMeasure, dMeasureLevel,
-		dReplayOff, dReplayTime, dReplayFlag;
+		dReplayOff, dReplayTime, dReplayFlag, dReplayLinOff, dReplayLin;
 	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dOutRaw, dWs, dRemaining;
 	int *hRemaining = nullptr;      /* pinned */
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -152,7 +154,7 @@ struct _simcu {
 	{
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
 			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder, &dOrder2, &dMeasure,
-			&dMeasureLevel, &dReplayOff, &dReplayTime, &dReplayFlag, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
+			&dMeasureLevel, &dReplayOff, &dReplayTime, &dReplayFlag, &dReplayLinOff, &dReplayLin, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
 			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dOutRaw,
 			&dWs, &dRemaining};
 		for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) all[i]->release();
@@ -536,8 +538,9 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "max_blocks_per_sm") r->maxBlocksPerSM = (int)value;
 	else if (n == "claim_below") r->claimBelow = std::max(0, std::min(31, (int)value));
 	else if (n == "replay") r->replay = (value != 0.0);
-	else if (n == "block_sync") r->blockSync = (value != 0.0);
+	else if (n == "block_sync") r->blockSync = (value < 0.0) ? -1 : (value != 0.0);
 	else if (n == "growth_limit") r->growthLimit = value;
+	else if (n == "tline_prefetch") r->tlinePrefetch = (value != 0.0);
 	else return fail("unknown option %s", name);
 	r->prepared = false;
 	return 0;
@@ -555,11 +558,18 @@ int simcuSetPivots(simcu_ *r, int phase, const int *pc, const int *pr, int n)
 	return 0;
 }
 
-int simcuSetReplayLog(simcu_ *r, const int *offsets, const double *times, const int *flags)
+int simcuSetReplayLog(simcu_ *r, const int *offsets, const double *times, const int *flags,
+		const int *linOffsets, const int *linMasks)
 {
 	if (!r) return -1;
 	r->replayOff.clear(); r->replayTime.clear(); r->replayFlag.clear();
-	if (offsets && times && flags) {
+	r->replayLinOff.clear(); r->replayLin.clear();
+	if (offsets && times && flags && linOffsets && linMasks) {
+		if (linOffsets[0] != 0) return fail("replay log: linOffsets[0] must be 0");
+		for (int i = 0; i < r->M; i++)
+			if (linOffsets[i + 1] < linOffsets[i]) return fail("replay log: offsets must not decrease");
+		r->replayLinOff.assign(linOffsets, linOffsets + r->M + 1);
+		r->replayLin.assign(linMasks, linMasks + linOffsets[r->M]);
 		if (offsets[0] != 0) return fail("replay log: offsets[0] must be 0");
 		for (int i = 0; i < r->M; i++)
 			if (offsets[i + 1] < offsets[i]) return fail("replay log: offsets must not decrease");
@@ -732,7 +742,7 @@ int pilotPass(simcu_ *r, bool needOP, bool needTran)
 				b.S.reserve(std::max(1, p.stateDoubles) * m8) ||
 				b.IS.reserve(std::max(1, p.stateInts) * m4) || b.CD.reserve(CD_NUM * m8) ||
 				b.CI.reserve(CI_NUM * m4) || b.Ht.reserve(R * m8) ||
-				b.Hx.reserve((size_t)R * (nh + 1) * m8) || b.remaining.reserve(sizeof(int)))
+				b.Hx.reserve((size_t)R * std::max(1, nh) * m8) || b.remaining.reserve(sizeof(int)))
 			break;
 		if (cudaMemset(b.S.p, 0, std::max(1, p.stateDoubles) * m8) != cudaSuccess ||
 				cudaMemset(b.IS.p, 0, std::max(1, p.stateInts) * m4) != cudaSuccess)
@@ -778,7 +788,7 @@ int buildJitKernel(simcu_ *r)
 {
 	JitConfig cfg;
 	cfg.threadsPerBlock = r->tpb; cfg.minBlocks = r->minBlocksUsed; cfg.gmin = r->ctl.gmin;
-	cfg.replay = r->replay; cfg.blockSync = r->blockSync; cfg.growthLimit = r->growthLimit;
+	cfg.replay = r->replay; cfg.blockSync = r->blockSyncUsed; cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch;
 	if (r->jit && r->jitProbes == r->probeRows && r->jitCfg == cfg && r->jitMeasures == r->measures)
 		return 0;
 	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows,
@@ -904,7 +914,8 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		if (r->interpreter) return fail("replay needs the specialised kernel (interpreter = 0)");
 		if ((int)r->replayOff.size() != M + 1) return fail("replay = 1 without a log (simcuSetReplayLog)");
 		if (r->dReplayOff.upload(r->replayOff) || r->dReplayTime.upload(r->replayTime) ||
-				r->dReplayFlag.upload(r->replayFlag))
+				r->dReplayFlag.upload(r->replayFlag) || r->dReplayLinOff.upload(r->replayLinOff) ||
+				r->dReplayLin.upload(r->replayLin))
 			return -1;
 	}
 	for (int ph = 0; ph < 2; ph++) {
@@ -912,6 +923,7 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		a.claimBelow = r->claimBelow;
 		a.replayOff = r->dReplayOff.as<int>(); a.replayTime = r->dReplayTime.as<double>();
 		a.replayFlag = r->dReplayFlag.as<int>();
+		a.replayLinOff = r->dReplayLinOff.as<int>(); a.replayLin = r->dReplayLin.as<int>();
 	}
 	int sms = 148, dev = 0;
 	CU(cudaGetDevice(&dev));
@@ -937,15 +949,35 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 				r->dIS.reserve(std::max(1, p.stateInts) * m4) || r->dCD.reserve(CD_NUM * m8))
 			return -1;
 	} else {
-		r->tpb = r->tpbOpt > 0 ? std::max(32, (r->tpbOpt / 32) * 32) : 64;
 		r->wsShared = 0;
-		/* Register budget (measured on B200): a batch that fits the machine at
-		 * 255 registers per thread is latency-bound and wants them all; a larger
-		 * batch of a SMALL circuit gains more from twice the resident warps
-		 * (128 registers); mid-size circuits (IBIS links) spill too much there. */
+		/* Launch shape (measured on B200, profiles/): the kernel is bound by the
+		 * latency of its own spilled state and of the T-line history, never by
+		 * HBM bandwidth, and its loop body is several times the instruction cache.
+		 *  - a batch that does not fill the machine: 64-thread blocks spread over
+		 *    all SMs, every register the compiler wants (one instance's latency);
+		 *  - a full machine: the warps of a block start every attempt together
+		 *    (block_sync) and share instruction-cache lines - one block per SM;
+		 *  - a working set far beyond the register file (cfg5: 763 doubles per
+		 *    instance) gains more from 32 resident warps at 64 registers than from
+		 *    255 registers at 8 warps; mid-size circuits (cfg4: 434) the opposite;
+		 *  - small circuits (N <= 12) in big batches: 128 registers, 16 warps. */
+		const int workingSet = p.stateDoubles + p.nnzA + 3 * p.N + (int)p.pmap.size();
+		const bool full = (long long)M >= (long long)sms * 256;
+		int sync = r->blockSync;
 		r->minBlocksUsed = r->minBlocks;
+		if (r->tpbOpt > 0) {
+			r->tpb = std::min(1024, std::max(32, (r->tpbOpt / 32) * 32));
+			if (sync < 0) sync = 0;
+		} else if (full && p.N > 12) {
+			r->tpb = (workingSet >= 600) ? 1024 : 256;
+			if (sync < 0) sync = 1;
+		} else {
+			r->tpb = 64;
+			if (sync < 0) sync = 0;
+		}
 		if (r->minBlocks == 0 && p.N <= 12 && (long long)M > (long long)sms * 4 * r->tpb)
 			r->minBlocksUsed = 65536 / (128 * r->tpb);
+		r->blockSyncUsed = sync;
 		if (buildJitKernel(r)) return -1;
 		/* active lanes per warp */
 		const int wpb = r->tpb / 32;
@@ -958,9 +990,12 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		 * warps thrash L1 with their local-memory windows - so 32 unless asked) */
 		int pow2 = 1;
 		while (pow2 * 2 <= lanes) pow2 *= 2;
-		r->lanes = r->blockSync ? 32 : pow2;      /* the block barrier needs every thread */
+		r->lanes = r->blockSyncUsed ? 32 : pow2;      /* the block barrier needs every thread */
 		const long long warps = ((long long)M + r->lanes - 1) / r->lanes;
-		const long long want = (warps + wpb - 1) / wpb;
+		long long want = (warps + wpb - 1) / wpb;
+		/* fewer blocks than SMs: spread the warps over all of them (lanes claim
+		 * their instances one by one, surplus lanes stay idle) */
+		if (want < sms) want = std::min<long long>(sms, warps);
 		r->jitBlocks = (int)std::max(1LL, std::min(want, capacity / wpb));
 		slots = r->jitBlocks * wpb * r->lanes;
 		r->args[0].lanes = r->args[1].lanes = r->lanes;
@@ -979,7 +1014,7 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		}
 	}
 	r->histRecords = R;
-	if (r->dHx.reserve((size_t)R * (nh + 1) * slots * 8)) return -1;
+	if (r->dHt.reserve((size_t)R * slots * 8) || r->dHx.reserve((size_t)R * std::max(1, nh) * slots * 8)) return -1;
 	for (int ph = 0; ph < 2; ph++) {
 		SimcuArgs &a = r->args[ph];
 		a.histRecords = R;
@@ -1314,7 +1349,8 @@ int simcuFetchCounters(simcu_ *r, char *which, int *out)
 	static const struct { const char *name; int row; } rows[] = {
 		{"status", CI_STATUS}, {"accepted", CI_ACCEPTED}, {"rejected_lte", CI_REJ_LTE},
 		{"rejected_nc", CI_REJ_NC}, {"factorizations", CI_NFACT}, {"op_factorizations", CI_NFACT_OP},
-		{"pivot_breakdowns", CI_BREAK}, {"replay_diff", CI_REPLAY_DIFF}, {"pivot_growth", CI_GROWTH}};
+		{"pivot_breakdowns", CI_BREAK}, {"replay_diff", CI_REPLAY_DIFF}, {"pivot_growth", CI_GROWTH},
+		{"linearize_diff", CI_LIN_DIFF}};
 	for (size_t i = 0; i < sizeof rows / sizeof rows[0]; i++)
 		if (!std::strcmp(which, rows[i].name)) {
 			CU(cudaMemcpy(out, r->dCI.as<int>() + (size_t)rows[i].row * r->M, (size_t)r->M * 4,
@@ -1484,6 +1520,7 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	const std::vector<double> consts[2] = {p.constOP, p.constTran};
 	JitConfig cfg;
 	cfg.threadsPerBlock = tpb; cfg.minBlocks = r->minBlocks; cfg.gmin = r->ctl.gmin; cfg.replay = r->replay;
+	cfg.blockSync = (r->blockSync > 0); cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch;
 	const std::string src = assembleSource(p, sched, active, consts, probeRows, r->measures, cfg);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;

@@ -447,7 +447,7 @@ bool inPhase(const int *rec, int phase)
 	}
 }
 
-void emitPhases(Out &o, const Program &p)
+void emitPhases(Out &o, const Program &p, bool tlinePrefetch)
 {
 	static const char *const head[7] = {
 		"DEV void genLoad(Inst &c)\n{\n",
@@ -473,6 +473,18 @@ void emitPhases(Out &o, const Program &p)
 			for (int k = 0; k < p.ndev; k++) any = any || inPhase(&p.dev[(size_t)k * SIMCU_DEV_STRIDE], 3);
 			if (any) o.f("\titBegin(c);\n");
 		}
+		if (ph == 2 && tlinePrefetch) {
+			/* step: with several T-lines, a first pass locates every line's delayed
+			 * time and prefetches the records, so their DRAM latencies overlap */
+			int nT = 0;
+			for (int k = 0; k < p.ndev; k++) nT += (p.dev[(size_t)k * SIMCU_DEV_STRIDE + DF_TYPE] == DK_T);
+			if (nT >= 2 && !p.histRows.empty())
+				for (int k = 0; k < p.ndev; k++) {
+					if (p.dev[(size_t)k * SIMCU_DEV_STRIDE + DF_TYPE] != DK_T) continue;
+					emitRecord(o, p, k);
+					o.f(" tlinePrefetch(c, d); }\n");
+				}
+		}
 
 		for (int k = 0; k < p.ndev; k++) {
 			if (!inPhase(&p.dev[(size_t)k * SIMCU_DEV_STRIDE], ph)) continue;
@@ -485,7 +497,7 @@ void emitPhases(Out &o, const Program &p)
 
 /* ---- numeric LU + solves, straight-line --------------------------------------- */
 void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vector<char> &active,
-		const std::vector<double> &cst, int phase)
+		const std::vector<double> &cst, int phase, bool guard)
 {
 	const int N = p.N, F = s.F;
 	o.f("/* %s: %d unknowns, %d matrix slots (%d fill), %d L + %d U off-diagonal entries */\n",
@@ -531,7 +543,7 @@ void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vec
 			const int *e = lrow + r * (2 + nU);
 			/* growth guard: the fixed sequence was chosen on pilot instances; a
 			 * multiplier this large means the pivot has lost that many digits */
-			o.f("\t{ const double l = w%d * i%d; grow |= (fabs(l) > SIMCU_LMAX);", e[0], k);
+			o.f("\t{ const double l = w%d * i%d;%s", e[0], k, guard ? " grow |= (fabs(l) > SIMCU_LMAX);" : "");
 			for (int j = 0; j < nU; j++) o.f(" w%d -= l * w%d;", e[2 + j], u[2 * j]);
 			o.f(" y%d -= l * y%d; }\n", e[1] - F, yk);
 		}
@@ -588,14 +600,15 @@ std::string generatePrelude(const Program &p, int numProbes, int numMeasures, co
 
 std::string generateTopology(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
-		const std::vector<int> &probeRows, const std::vector<int> &measures)
+		const std::vector<int> &probeRows, const std::vector<int> &measures, bool growthGuard,
+		bool tlinePrefetch)
 {
 	Out o;
 	o.f("/* ---- generated for this netlist by simcu_codegen.cpp ---- */\n");
 	emitCalcAll(o, p);
-	emitPhases(o, p);
-	emitFactorSolve(o, p, sched[0], active[0], consts[0], 0);
-	emitFactorSolve(o, p, sched[1], active[1], consts[1], 1);
+	emitPhases(o, p, tlinePrefetch);
+	emitFactorSolve(o, p, sched[0], active[0], consts[0], 0, growthGuard);
+	emitFactorSolve(o, p, sched[1], active[1], consts[1], 1, growthGuard);
 	emitRows(o, "genHistRows", p.histRows);
 	emitRows(o, "genProbeRows", probeRows);
 	/* measures: (kind, row) pairs; the level comes from the kernel arguments */

@@ -19,11 +19,13 @@ struct JitConfig {
 	double gmin = 1e-15;      /* guard of every calculon division, folded into the code */
 	int replay = 0;           /* 1: replay an attempt log instead of own step control (tests) */
 	int blockSync = 0;        /* 1: the warps of a block start every attempt together */
-	double growthLimit = 1e6; /* LU multipliers above this are counted (pivot growth guard) */
+	double growthLimit = 1e6; /* LU multipliers above this are counted (pivot growth guard; <= 0: off) */
+	int tlinePrefetch = 1;    /* circuits with >= 2 T-lines: locate + prefetch pass before the step */
 	bool operator==(const JitConfig &o) const
 	{
 		return threadsPerBlock == o.threadsPerBlock && minBlocks == o.minBlocks && gmin == o.gmin &&
-			replay == o.replay && blockSync == o.blockSync && growthLimit == o.growthLimit;
+			replay == o.replay && blockSync == o.blockSync && growthLimit == o.growthLimit &&
+			tlinePrefetch == o.tlinePrefetch;
 	}
 };
 
@@ -32,7 +34,8 @@ std::string generatePrelude(const Program &p, int numProbes, int numMeasures, co
 /* device records, expressions and the unrolled LU of both phases */
 std::string generateTopology(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
-		const std::vector<int> &probeRows, const std::vector<int> &measures);
+		const std::vector<int> &probeRows, const std::vector<int> &measures, bool growthGuard,
+		bool tlinePrefetch);
 /* prelude + embedded library headers + topology + kernel */
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],

@@ -63,6 +63,9 @@ struct Inst {
 	int order;
 	int err;             /* SIMCU_ERR_* of this instance (0 = ok) */
 	int growth;          /* factorisations with an LU multiplier above SIMCU_LMAX */
+	/* replay (test instrumentation): logged outcomes of the convergence tests of
+	 * this linearize pass, next bit to consume, own decisions that differed */
+	mutable int linMask, linBit, linDiff;
 	mutable double Av[SIMCU_DIM(SIMCU_NNZ)], Bv[SIMCU_DIM(SIMCU_N)];
 	mutable double Xv[SIMCU_DIM(SIMCU_N)], Xa[SIMCU_DIM(SIMCU_N)];
 	mutable double sv[SIMCU_DIM(SIMCU_SD)];
@@ -254,7 +257,7 @@ DEV double pwGetNextX(const Table &t, int &index, double x0)
  * angles if those are more than 1e-3 away from the threshold, and only then from
  * the two double-precision atan2 of the reference.  The decision is the
  * reference's in every case; its cost is a handful of compares. */
-DEV int cbAngleBreak(double dy0, double dx0, double dy1, double dx1, double maxAngle)
+DEVFN int cbAngleBreak(double dy0, double dx0, double dy1, double dx1, double maxAngle)
 {
 	if (maxAngle > 0.93 && maxAngle < 1.10) {
 		const double a0 = fabs(dy0), a1 = fabs(dy1);
@@ -339,10 +342,20 @@ DEV int clIsLinear(const Inst &c, int sLast, int iState, double tol, double V,
 {
 	const double reltol = c.a.ctl.reltol;
 	const double lastV = c.S(sLast);
-	double e = reltol * MaxAbs(lastV, V) + tol;
-	if (fabs(lastV - V) > e) { c.IS(iState) = 0; c.S(sLast) = V; return 0; }
-	e = reltol * MaxAbs(calcedV, V) + tol;
-	if (fabs(calcedV - V) > e) { c.IS(iState) = 0; c.S(sLast) = V; return 0; }
+	const double e1 = reltol * MaxAbs(lastV, V) + tol;
+	const double e2 = reltol * MaxAbs(calcedV, V) + tol;
+	bool passed = !(fabs(lastV - V) > e1) && !(fabs(calcedV - V) > e2);
+#if defined(SIMCU_JIT) && SIMCU_REPLAY
+	/* replay: these two threshold tests at reltol are what a 1-ulp difference can
+	 * flip; take the oracle's outcome and count the disagreements */
+	{
+		const bool logged = ((c.linMask >> c.linBit) & 1) != 0;
+		c.linBit++;
+		if (logged != passed) c.linDiff++;
+		passed = logged;
+	}
+#endif
+	if (!passed) { c.IS(iState) = 0; c.S(sLast) = V; return 0; }
 	c.S(sLast) = V;
 	const int st = c.IS(iState);
 	if (st == 1) { c.IS(iState) = 2; return 1; }
@@ -949,11 +962,12 @@ DEV void devInitStep(Inst &c, const int *d)
 DEV int tlineWrap(int p, int R) { return (p >= R) ? p - R : ((p < 0) ? p + R : p); }
 
 /* Finds the two history records that bracket (or, past the newest record,
- * precede) the delayed time tp.  ring = this thread's records, `rec` doubles
- * each, column 0 = time; record q lives at position q % R.  Returns (hint,
- * position of the earlier record, position of the later one, position of the
- * hint record + 1 or 0 = the needed record is gone).  One modulo per call. */
-DEVFN int4 tlineLocateFn(const double *ring, int R, int rec, int count, int hint, double tp)
+ * precede) the delayed time tp.  times = this thread's record TIMES (dense, one
+ * double per record: a walk of +-16 records stays inside one or two cache
+ * lines); record q lives at position q % R.  Returns (hint, position of the
+ * earlier record, position of the later one, position of the hint record + 1
+ * or 0 = the needed record is gone).  One modulo per call. */
+DEVFN int4 tlineLocateFn(const double *times, int R, int count, int hint, double tp)
 {
 	int4 r;
 	r.x = hint; r.y = 0; r.z = 0; r.w = 0;
@@ -962,7 +976,7 @@ DEVFN int4 tlineLocateFn(const double *ring, int R, int rec, int count, int hint
 	if (i < lo || i >= count) i = lo;
 	const int i0 = i, base = i % R;
 	/* time of record j in [lo, count): |j - i0| < R, so one wrap at most */
-	#define HTIME(j) ring[(size_t)tlineWrap(base + ((j) - i0), R) * rec]
+	#define HTIME(j) times[tlineWrap(base + ((j) - i0), R)]
 	/* The reference walks record by record from the hint (history_interp.c:
 	 * 42-92).  Accepted times increase strictly, so the record it lands on is
 	 * THE largest j with t_j <= tp; a galloping + binary search finds the same j
@@ -1004,9 +1018,42 @@ DEVFN int4 tlineLocateFn(const double *ring, int R, int rec, int count, int hint
 DEV double tlineInterp(const double *recP, const double *recN, int col, double tP, double tN, double tp)
 {
 	if (col < 0) return 0.0;
-	const double xP = recP[1 + col], xN = recN[1 + col];
+	const double xP = recP[col], xN = recN[col];
 	return ((xN - xP) / (tN - tP)) * (tp - tP) + xP;
 }
+
+#ifdef SIMCU_JIT
+/* First pass over the T-lines of an attempt (specialised kernel, circuits with
+ * several lines): locate the delayed time of this line, remember the landing
+ * record as the hint, and ask L2 for the sectors of the two records the second
+ * pass (devStep) will interpolate - so the DRAM latencies of all lines overlap
+ * instead of adding up, one dependent round trip after the other.  The hint only
+ * shortens the search (same landing record), so results do not change. */
+DEV void tlinePrefetch(Inst &c, const int *d)
+{
+	const int ib = d[DF_IBASE];
+	const double tp = c.time - c.P(d[DF_PTD]);
+	if (!(tp > 0)) return;
+	const int R = c.a.histRecords, nh = SIMCU_NH;
+	const double *times = c.a.Ht + (size_t)c.hslot * R;
+	const double *vals = c.a.Hx + (size_t)c.hslot * R * nh;
+	const int4 r = tlineLocateFn(times, R, c.hcount, c.IS(ib + 2), tp);
+	if (!r.w) return;
+	c.IS(ib + 2) = r.x;
+	const int *h = d + DF_TH0;
+	int lo = nh, hi = -1;
+	SIMCU_UNROLL
+	for (int k = 0; k < 6; k++) if (h[k] >= 0) { lo = (h[k] < lo) ? h[k] : lo; hi = (h[k] > hi) ? h[k] : hi; }
+	if (hi < 0) return;
+	const double *p0 = vals + (size_t)r.y * nh, *p1 = vals + (size_t)r.z * nh;
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + lo));
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(p1 + lo));
+	if ((hi - lo) >= 4) {
+		asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + hi));
+		asm volatile("prefetch.global.L2 [%0];" :: "l"(p1 + hi));
+	}
+}
+#endif
 
 DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 {
@@ -1041,13 +1088,18 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 			Vk = c.S(sb + 2); Vj = c.S(sb + 3); Vl = c.S(sb + 4); Vm = c.S(sb + 5);
 		} else {
 			const int *h = d + DF_TH0;              /* R S K J L M */
-			const int rec = c.a.nh + 1;
-			const double *ring = c.a.Hx + (size_t)c.hslot * c.a.histRecords * rec;
-			const int4 r = tlineLocateFn(ring, c.a.histRecords, rec, c.hcount, c.IS(ib + 2), tp);
+#ifdef SIMCU_JIT
+			const int nh = SIMCU_NH, R = c.a.histRecords;
+#else
+			const int nh = c.a.nh, R = c.a.histRecords;
+#endif
+			const double *times = c.a.Ht + (size_t)c.hslot * R;
+			const double *vals = c.a.Hx + (size_t)c.hslot * R * nh;
+			const int4 r = tlineLocateFn(times, R, c.hcount, c.IS(ib + 2), tp);
 			if (!r.w) { c.err = SIMCU_ERR_HISTORY; return 0; }
 			c.IS(ib + 2) = r.x;
-			const double *recP = ring + (size_t)r.y * rec, *recN = ring + (size_t)r.z * rec;
-			const double tP = recP[0], tN = recN[0];
+			const double *recP = vals + (size_t)r.y * nh, *recN = vals + (size_t)r.z * nh;
+			const double tP = times[r.y], tN = times[r.z];
 			Ir = tlineInterp(recP, recN, h[0], tP, tN, tp); Is = tlineInterp(recP, recN, h[1], tP, tN, tp);
 			Vk = tlineInterp(recP, recN, h[2], tP, tN, tp); Vj = tlineInterp(recP, recN, h[3], tP, tN, tp);
 			Vl = tlineInterp(recP, recN, h[4], tP, tN, tp); Vm = tlineInterp(recP, recN, h[5], tP, tN, tp);
@@ -1265,10 +1317,11 @@ DEV void recordStep(Inst &c, const int *rows, double tNow)
 {
 	const SimcuArgs &a = c.a;
 	if (a.nh > 0 && a.histRecords > 0) {
-		double *rec = a.Hx + ((size_t)c.hslot * a.histRecords + c.hcount % a.histRecords) * (a.nh + 1);
-		rec[0] = tNow;
+		const size_t at = (size_t)c.hslot * a.histRecords + c.hcount % a.histRecords;
+		a.Ht[at] = tNow;
+		double *rec = a.Hx + at * SIMCU_NH_LOOP;
 		SIMCU_UNROLL
-		for (int j = 0; j < SIMCU_NH_LOOP; j++) rec[1 + j] = c.X(LDI(&rows[j]));
+		for (int j = 0; j < SIMCU_NH_LOOP; j++) rec[j] = c.X(LDI(&rows[j]));
 		c.hcount++;
 	}
 	if (a.rawMaxPoints > 0 && c.i >= a.rawFirst && c.i < a.rawFirst + a.rawCount) {

@@ -59,6 +59,7 @@ DEV void jitFinish(const SimcuArgs &a, Inst &c, const double *meas, int accepted
 	ci[(size_t)CI_NPTS * M] = c.npts;
 	ci[(size_t)CI_BREAK * M] = pivotBreaks;
 	ci[(size_t)CI_REPLAY_DIFF * M] = replayDiff;
+	ci[(size_t)CI_LIN_DIFF * M] = c.linDiff;
 	ci[(size_t)CI_GROWTH * M] = c.growth;
 }
 
@@ -89,7 +90,7 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 	bool exhausted = false;      /* this lane found the queue empty */
 	const unsigned lanesMask = (a.lanes >= 32) ? 0xffffffffu : ((1u << a.lanes) - 1u);
 #if SIMCU_REPLAY
-	int rp = 0, rpEnd = 0, rflag = 0, nfact0 = 0;
+	int rp = 0, rpEnd = 0, rflag = 0, nfact0 = 0, rl = 0;
 #endif
 
 	for (;;) {
@@ -146,6 +147,8 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 				transient = false;
 #if SIMCU_REPLAY
 				rp = __ldg(&a.replayOff[inst]); rpEnd = __ldg(&a.replayOff[inst + 1]);
+				rl = __ldg(&a.replayLinOff[inst]);
+				c.linDiff = 0;
 #endif
 				genLoad(c);                                 /* simulator.c:121-123 */
 				busy = true;
@@ -202,6 +205,11 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 				}
 				if (c.err) break;
 				if (count++ >= limit) break;
+#if SIMCU_REPLAY
+				c.linMask = (rl < __ldg(&a.replayLinOff[c.i + 1])) ? a.replayLin[rl] : 0;
+				c.linBit = 0;
+				rl++;
+#endif
 				const int linear = genLinearize(c);
 				if (c.err || linear) break;
 			}

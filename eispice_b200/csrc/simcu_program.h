@@ -92,7 +92,7 @@ enum {
 enum {
 	CI_ORDER = 0, CI_STATUS, CI_DONE, CI_ACCEPTED, CI_REJ_LTE, CI_REJ_NC,
 	CI_NFACT, CI_NFACT_OP, CI_NPTS, CI_HCOUNT, CI_GRIDIDX, CI_ATTEMPTS,
-	CI_BREAK, CI_REPLAY_DIFF, CI_GROWTH, CI_NUM
+	CI_BREAK, CI_REPLAY_DIFF, CI_GROWTH, CI_LIN_DIFF, CI_NUM
 };
 
 /* options of the loop: reference include/control.h:34-56 */
@@ -137,7 +137,7 @@ typedef struct {
 	/* per-instance state, all [slot][M] */
 	double *A, *B, *X, *Xrec, *S, *CD;
 	int *IS, *CI;
-	double *Ht, *Hx;          /* T-line history: Hx[thread][R][1 + nh], column 0 = time */
+	double *Ht, *Hx;          /* T-line history ring: times Ht[thread][R], values Hx[thread][R][nh] */
 	double *outGrid;          /* [ngrid][nprobes][M] */
 	double *outRaw;           /* [rawMaxPoints][N+1][rawCount] */
 	double *outMeasure;       /* [nmeasures][M]: device-side post-processing */
@@ -158,6 +158,10 @@ typedef struct {
 	const int *replayOff;
 	const double *replayTime;
 	const int *replayFlag;
+	/* ... and of the per-device convergence-test outcomes: one word per linearize
+	 * pass, entries [replayLinOff[i], replayLinOff[i+1]) of instance i */
+	const int *replayLinOff;
+	const int *replayLin;
 } SimcuArgs;
 
 #endif

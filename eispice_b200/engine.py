@@ -91,7 +91,7 @@ def lib():
     L.simcuSetInstanceTableSet.argtypes = [vp, cp, vp, C.c_int]
     L.simcuSetOption.argtypes = [vp, cp, C.c_double]
     L.simcuSetPivots.argtypes = [vp, C.c_int, vp, vp, C.c_int]
-    L.simcuSetReplayLog.argtypes = [vp, vp, vp, vp]
+    L.simcuSetReplayLog.argtypes = [vp, vp, vp, vp, vp, vp]
     L.simcuRunTransient.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int,
                                     C.c_int, vp, vp, ip, ip]
     L.simcuRunOperatingPoint.argtypes = [vp, C.c_int, vp, vp, ip, ip]
@@ -298,20 +298,29 @@ class Engine:
         self.L.simcuSetPivots(self.h, phase, pc.ctypes.data, pr.ctypes.data, len(pc))
 
     def set_replay_log(self, logs):
-        """Test instrumentation: logs[i] = (times, flags) of instance i as the CPU
-        oracle recorded them (tests/backends.py: OracleSim.attempt_log); the run
-        then replays those attempts instead of its own step control."""
+        """Test instrumentation: logs[i] = (times, flags, linearize masks) of
+        instance i as the CPU oracle recorded them (tests/backends.py:
+        OracleSim.attempt_log / linearize_log); the run then replays those attempts
+        and convergence-test outcomes instead of deciding itself."""
         if logs is None:
-            self.L.simcuSetReplayLog(self.h, None, None, None)
+            self.L.simcuSetReplayLog(self.h, None, None, None, None, None)
             self.set_option("replay", 0)
             return
         if len(logs) != self.num_instances:
             raise ValueError("one attempt log per instance")
         off = np.zeros(self.num_instances + 1, dtype=np.int32)
-        off[1:] = np.cumsum([len(t) for t, _ in logs])
-        times = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.float64) for t, _ in logs]))
-        flags = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.int32) for _, f in logs]))
-        if self.L.simcuSetReplayLog(self.h, off.ctypes.data, times.ctypes.data, flags.ctypes.data):
+        off[1:] = np.cumsum([len(x[0]) for x in logs])
+        times = np.ascontiguousarray(np.concatenate([np.asarray(x[0], dtype=np.float64) for x in logs]))
+        flags = np.ascontiguousarray(np.concatenate([np.asarray(x[1], dtype=np.int32) for x in logs]))
+        loff = np.zeros(self.num_instances + 1, dtype=np.int32)
+        loff[1:] = np.cumsum([len(x[2]) for x in logs])
+        lin = np.ascontiguousarray(np.concatenate([np.asarray(x[2], dtype=np.int32) for x in logs]))
+        if len(lin) == 0:
+            lin = np.zeros(1, dtype=np.int32)
+        if len(times) == 0:
+            times, flags = np.zeros(1), np.zeros(1, dtype=np.int32)
+        if self.L.simcuSetReplayLog(self.h, off.ctypes.data, times.ctypes.data, flags.ctypes.data,
+                                    loff.ctypes.data, lin.ctypes.data):
             raise ValueError("bad replay log")
         self.set_option("replay", 1)
 

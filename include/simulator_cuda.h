@@ -161,8 +161,14 @@ int simcuSetPivots(simcu_ *r, int phase, const int *pc, const int *pr, int n);
  * accepted, 1 rejected by the LTE test, 2 rejected for non-convergence.  The
  * log comes from the CPU oracle (oracle/eis_oracle.h: eoGetAttemptLog), so that
  * both sides take identical steps and every unknown of every accepted step can
- * be held to 1e-6 / 1e-9.  Copied immediately; offsets = NULL clears it. */
-int simcuSetReplayLog(simcu_ *r, const int *offsets, const double *times, const int *flags);
+ * be held to 1e-6 / 1e-9.  linMasks[linOffsets[i] .. linOffsets[i+1]) holds one
+ * word per linearize pass of instance i (operating point first): bit k = the
+ * two convergence tests of its k-th nonlinear device passed
+ * (math/checklinear.c:62-77) - those threshold decisions are replayed too, and
+ * the engine's own are counted where they differ (counter linearize_diff).
+ * Copied immediately; offsets = NULL clears it. */
+int simcuSetReplayLog(simcu_ *r, const int *offsets, const double *times, const int *flags,
+		const int *linOffsets, const int *linMasks);
 
 /* ---- runs ----------------------------------------------------------------- */
 /* simulatorRunTransient (simulator.h:35-38) for ONE instance (index
@@ -259,7 +265,8 @@ int simcuSetMeasures(simcu_ *r, char *probes[], const int *kinds, const double *
 int simcuFetchMeasures(simcu_ *r, double *out);
 /* per-instance counters of the last batch into out[numInstances]; which is
  * status, accepted, rejected_lte, rejected_nc, factorizations,
- * op_factorizations, pivot_breakdowns, replay_diff or pivot_growth */
+ * op_factorizations, pivot_breakdowns, replay_diff, linearize_diff or
+ * pivot_growth */
 int simcuFetchCounters(simcu_ *r, char *which, int *out);
 /* raw (time, X) record of one instance of the last batch, reference layout
  * (core/matrix.c:430-470): malloc'd [numPoints][numVariables], column 0 = time.

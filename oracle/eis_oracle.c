@@ -672,14 +672,20 @@ typedef struct { char state; char units; double lastV; } CheckLinear;
 
 static void clInitialize(CheckLinear *r, double ic) { r->state = 'a'; r->lastV = ic; }
 
+/* outcome of the two tolerance tests of the last clIsLinear call (1 = both
+ * passed); read by the attempt log (test instrumentation) */
+static int g_clPassed;
+
 static int clIsLinear(CheckLinear *r, const Control *c, double V, double calcedV)
 {
 	double tol = (r->units == 'V') ? c->vntol
 		: (r->units == 'A') ? c->abstol : c->captol;
 	double e = c->reltol * MaxAbs(r->lastV, V) + tol;
+	g_clPassed = 0;
 	if (fabs(r->lastV - V) > e) { r->state = 'a'; r->lastV = V; return 0; }
 	e = c->reltol * MaxAbs(calcedV, V) + tol;
 	if (fabs(calcedV - V) > e) { r->state = 'a'; r->lastV = V; return 0; }
+	g_clPassed = 1;
 	r->lastV = V;
 	if (r->state == 'b') { r->state = 'c'; return 1; }
 	if (r->state == 'c') return 1;
@@ -995,6 +1001,9 @@ struct eo_sim {
 	/* attempt log (tests only): one entry per transient attempt, in order */
 	int logOn, logN, logCap;
 	double *logTime; int *logFlag;
+	/* per linearize pass (simulatorSolve :57-58), operating point included: bit k =
+	 * the tolerance tests of the k-th nonlinear device passed (checklinear.c:62-77) */
+	int linN, linCap; int *linMask;
 };
 
 /* --- rows & pattern: core/row.c:46-66,163-204, core/matrix.c:292-346 ------ */
@@ -1112,7 +1121,7 @@ void eoDestroy(eo_sim *s)
 	free(s->rdone); free(s->cdone); free(s->prow); free(s->pcol); free(s->pinv);
 	free(s->htime); free(s->hX);
 	for (i = 0; i < 2; i++) { free(s->fixPc[i]); free(s->fixPr[i]); }
-	free(s->logTime); free(s->logFlag);
+	free(s->logTime); free(s->logFlag); free(s->linMask);
 	free(s);
 }
 void eoFree(void *p) { free(p); }
@@ -1816,6 +1825,7 @@ static int simSolve(eo_sim *s, int limit)
 	if (limit < 1) return -1;
 	TRY(luSolve(s));
 	while (count++ < limit) {
+		int mask = 0, bit = 0;
 		linear = 1;
 		for (i = 0; i < s->ndev; i++) {
 			int loc = 1;
@@ -1824,7 +1834,16 @@ static int simSolve(eo_sim *s, int limit)
 					d->type == D_BC) {
 				TRY(devLinearize(s, d, &loc));
 				linear = linear && loc;
+				if (bit < 31) mask |= g_clPassed << bit;
+				bit++;
 			}
+		}
+		if (s->logOn) {
+			if (s->linN == s->linCap) {
+				s->linCap = s->linCap ? 2 * s->linCap : 8192;
+				s->linMask = realloc(s->linMask, sizeof(int) * s->linCap);
+			}
+			s->linMask[s->linN++] = mask;
 		}
 		if (linear) break;
 		TRY(luSolve(s));
@@ -1967,7 +1986,13 @@ static void logAttempt(eo_sim *s, double time, int order, int outcome, int solve
 	s->logN++;
 }
 
-void eoSetAttemptLog(eo_sim *s, int on) { s->logOn = on; s->logN = 0; }
+void eoSetAttemptLog(eo_sim *s, int on) { s->logOn = on; s->logN = 0; s->linN = 0; }
+
+int eoGetLinearizeLog(eo_sim *s, const int **masks)
+{
+	if (masks) *masks = s->linMask;
+	return s->linN;
+}
 
 int eoGetAttemptLog(eo_sim *s, const double **times, const int **flags)
 {
@@ -1988,7 +2013,7 @@ int eoRunTransient(eo_sim *s, double tstep, double tstop, double tmax,
 	if (s == NULL) return -1;
 	c = &s->ctl;
 	memset(&s->st, 0, sizeof s->st);
-	s->logN = 0;
+	s->logN = 0; s->linN = 0;
 
 	if (tmax == 0.0) {                          /* :91-94 */
 		tmax = tstop / 50;

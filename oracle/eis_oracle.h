@@ -74,6 +74,11 @@ int eoSetPivots(eo_sim *s, int phase, const int *pc, const int *pr, int n);
 #define EO_LOG_FLAG(order, outcome, solves) ((order) | ((outcome) << 4) | ((solves) << 8))
 void eoSetAttemptLog(eo_sim *s, int on);
 int eoGetAttemptLog(eo_sim *s, const double **times, const int **flags);
+/* one word per linearize pass of the last transient (operating point first):
+ * bit k = both tolerance tests of the k-th nonlinear device (VI / B sources in
+ * netlist order) passed (math/checklinear.c:62-77) - the threshold decisions at
+ * reltol that a 1-ulp difference can flip.  At most 31 nonlinear devices. */
+int eoGetLinearizeLog(eo_sim *s, const int **masks);
 
 int eoRunTransient(eo_sim *s, double tstep, double tstop, double tmax,
 		int restart, double **data, char ***variables, int *numPoints,

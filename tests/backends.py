@@ -75,6 +75,7 @@ def oracle_lib():
                                    C.c_double, C.c_void_p, C.c_void_p]
         lib.eoSetAttemptLog.argtypes = [C.c_void_p, C.c_int]
         lib.eoGetAttemptLog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.eoGetLinearizeLog.argtypes = [C.c_void_p, C.c_void_p]
         _oracle = lib
     return _oracle
 
@@ -220,6 +221,15 @@ class OracleSim:
             return np.zeros(0), np.zeros(0, dtype=np.int32)
         return (np.ctypeslib.as_array(t, shape=(n,)).copy(),
                 np.ctypeslib.as_array(f, shape=(n,)).copy())
+
+    def linearize_log(self):
+        """One word per linearize pass (operating point first): bit k = the
+        convergence tests of the k-th nonlinear device passed."""
+        m = C.POINTER(C.c_int)()
+        n = self.lib.eoGetLinearizeLog(self.h, C.byref(m))
+        if n == 0:
+            return np.zeros(0, dtype=np.int32)
+        return np.ctypeslib.as_array(m, shape=(n,)).copy()
 
     def stats(self):
         st = EoStats()

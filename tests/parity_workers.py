@@ -29,7 +29,7 @@ def to_grid(data, tstep, tstop):
 
 def oracle_logged(args):
     """Oracle with a fixed pivot sequence (the GPU's) and the attempt log:
-    (raw record, log times, log flags), or None if the oracle aborts."""
+    (raw record, log times, log flags, linearize masks), or None if it aborts."""
     cfg, M, idx, piv = args
     import backends
     w = _workload(cfg, M)
@@ -44,7 +44,7 @@ def oracle_logged(args):
     except RuntimeError:
         return None
     t, f = o.attempt_log()
-    return d, t, f
+    return d, t, f, o.linearize_log()
 
 
 def gridded(args):

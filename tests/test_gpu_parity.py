@@ -542,3 +542,49 @@ def test_parameter_sweep_over_ten_decades_against_partial_pivoting():
         assert (np.abs(data2[::-1, :, p] - res.data[:, :, p]) <= tol).all()
     assert eng.stats()["jitCompiles"] >= jit0
     eng.close()
+
+
+def test_run_transient_batch_one_call_entry():
+    """simcuRunTransientBatch itself (the one-call entry a binding
+    would use): host parameter arrays in, malloc'd host result out, simcuFree;
+    equal to the staged Prepare / RunDevice / Fetch calls; restart = 0 after a
+    finished transient is refused loudly (core/simulator.c:111,138-140)."""
+    import ctypes as C
+    w = workloads.make("cfg1", 48)
+    eng = engine.Engine(w.cct.netlist(), w.M)
+    eng.set_params(w.params)
+    L = eng.L
+    probes = eng._probe_array(w.probes)
+    data, status = C.POINTER(C.c_double)(), C.POINTER(C.c_int)()
+    ngrid = C.c_int()
+    st = engine.Stats()
+    rc = L.simcuRunTransientBatch(eng.h, w.tstep, w.tstop, 0.0, 1, probes, len(w.probes),
+                                  C.byref(data), C.byref(ngrid), C.byref(status), C.byref(st))
+    assert rc == 0 and ngrid.value > 1 and st.accepted > 48 * 500 and st.failed == 0
+    got = np.ctypeslib.as_array(data, shape=(w.M, ngrid.value, len(w.probes))).copy()
+    stat = np.ctypeslib.as_array(status, shape=(w.M,)).copy()
+    L.simcuFree(data)
+    L.simcuFree(status)
+    assert (stat == 0).all()
+    # restart = 0 on a handle that has run a transient: refused, not ignored
+    d2, s2 = C.POINTER(C.c_double)(), C.POINTER(C.c_int)()
+    engine.lib().simcuSetOption(None, b"quiet", 1.0)
+    rc = L.simcuRunTransientBatch(eng.h, w.tstep, w.tstop, 0.0, 0, probes, len(w.probes),
+                                  C.byref(d2), C.byref(ngrid), C.byref(s2), None)
+    assert rc == -1 and not d2
+    names, npts, nvar = C.POINTER(C.c_char_p)(), C.c_int(), C.c_int()
+    rc = L.simcuRunTransient(eng.h, w.tstep, w.tstop, 0.0, 0, 0, C.byref(d2), C.byref(names),
+                             C.byref(npts), C.byref(nvar))
+    engine.lib().simcuSetOption(None, b"quiet", 0.0)
+    assert rc == -1
+    eng.close()
+    # the staged calls give the same numbers
+    eng2 = engine.Engine(w.cct.netlist(), w.M)
+    res = eng2.tran_batch(w.tstep, w.tstop, 0.0, w.params, w.probes)
+    assert np.array_equal(res.data, got)
+    # restart = 0 on a FRESH handle is a normal start (reference: restart || time == 0)
+    one = engine.Engine(w.cct.netlist(), 1)
+    d, v = one.tran_single(w.tstep, w.tstop, restart=False)
+    assert d.shape[0] > 500
+    one.close()
+    eng2.close()

@@ -70,7 +70,8 @@ def _replay(cfg, w, pick, sub, piv, pool, forced):
     (worst ratio or None when the oracle aborted), GPU status, replay diffs."""
     n = len(pick)
     logged = pool.map(pw.oracle_logged, [(cfg, w.M, int(i), piv) for i in pick])
-    logs = [(x[1], x[2]) if x is not None else (np.zeros(0), np.zeros(0, np.int32)) for x in logged]
+    logs = [(x[1], x[2], x[3]) if x is not None else (np.zeros(0), np.zeros(0, np.int32), np.zeros(0, np.int32))
+            for x in logged]
     eng = engine.Engine(w.cct.netlist(), n)
     if forced:
         eng.set_pivots(0, piv[0], piv[1])
@@ -81,7 +82,7 @@ def _replay(cfg, w, pick, sub, piv, pool, forced):
     assert all(np.array_equal(a, b) for a, b in zip(got, piv)), "GPU did not use the oracle's pivots"
     raws = eng.fetch_raw_all(CAP[cfg])
     diffs = eng.counters("replay_diff")
-    attempts = np.array([len(t) for t, _ in logs])
+    attempts = np.array([len(x[0]) for x in logs])
     eng.close()
     worst = [None if logged[j] is None else _tight(raws[j], logged[j][0]) for j in range(n)]
     return worst, res.status, diffs, attempts, logged

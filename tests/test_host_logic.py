@@ -325,13 +325,14 @@ def _host_lu_harness(src, tmp_path, phase):
 #include <cstring>
 #define DEV static inline
 #define SIMCU_ERR_SINGULAR 2
+#define SIMCU_LMAX 1e6
 using std::isfinite;
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
-struct Inst { double Av[%d], Bv[%d], Xv[%d]; int err; };
+struct Inst { double Av[%d], Bv[%d], Xv[%d]; int err, growth; };
 %s
 extern "C" int solve(const double *A, const double *B, double *X)
 {
-	Inst c; c.err = 0;
+	Inst c; c.err = 0; c.growth = 0;
 	std::memcpy(c.Av, A, sizeof c.Av); std::memcpy(c.Bv, B, sizeof c.Bv);
 	%s(c);
 	std::memcpy(X, c.Xv, sizeof c.Xv);

@@ -82,14 +82,15 @@ def main():
 
     # (2) replay
     ok = [j for j in range(n) if logged[j] is not None]
-    logs = [(logged[j][1], logged[j][2]) if logged[j] is not None else (np.zeros(0), np.zeros(0, np.int32))
-            for j in range(n)]
+    logs = [(logged[j][1], logged[j][2], logged[j][3]) if logged[j] is not None
+            else (np.zeros(0), np.zeros(0, np.int32), np.zeros(0, np.int32)) for j in range(n)]
     eng.set_replay_log(logs)
     t0 = time.time()
     res2 = eng.tran_batch(w.tstep, w.tstop, 0.0, sub, w.probes, raw_max_points=cap, raw_count=n)
     rep["gpu_replay_s"] = time.time() - t0
     raws2 = eng.fetch_raw_all(cap)
     diffs = eng.counters("replay_diff")
+    ldiffs = eng.counters("linearize_diff")
     worst_all, npass, nshape, bad = 0.0, 0, 0, []
     total = inside = 0
     for j in ok:
@@ -110,10 +111,12 @@ def main():
         else:
             k = np.unravel_index(np.argmax(r), r.shape)
             bad.append((int(pick[j]), "value", wj, int(k[0]), names[k[1] - 1] if k[1] else "time",
-                        float(od[k]), float(raws2[j][k]), int(diffs[j])))
+                        float(od[k]), float(raws2[j][k]), int(diffs[j]), int(ldiffs[j])))
     rep["replay"] = {"instances": len(ok), "pass_all_samples": npass, "shape_mismatch": nshape,
                      "worst_ratio": worst_all, "samples": total, "samples_inside": inside,
                      "replay_diffs_total": int(diffs.sum()), "instances_with_diffs": int((diffs > 0).sum()),
+                     "linearize_diffs_total": int(ldiffs.sum()), "instances_with_lin_diffs": int((ldiffs > 0).sum()),
+                     "linearize_passes": int(sum(len(x[2]) for x in logs)),
                      "status": np.bincount(res2.status).tolist(), "bad": bad[:20]}
     print(json.dumps(rep, indent=1))
     if out:
