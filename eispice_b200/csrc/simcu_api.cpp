@@ -116,7 +116,8 @@ struct _simcu {
 	int blockSync = -1;             /* warps of a block run their attempts in step (I-cache sharing); -1 = automatic */
 	int blockSyncUsed = 0;
 	double growthLimit = 1e6;       /* LU multiplier magnitude that counts as pivot growth */
-	int tlinePrefetch = 1;          /* locate + prefetch pass over the T-lines (>= 2 lines) */
+	int tlinePrefetch = 0;          /* locate + prefetch pass over the T-lines (>= 2 lines): measured slower */
+	int fmad = 1;                   /* 0: compile without a*b+c contraction (replay tests) */
 	std::vector<int> replayOff, replayFlag, replayLinOff, replayLin;
 	std::vector<double> replayTime;
 	std::vector<char> active[2];
@@ -541,6 +542,7 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "block_sync") r->blockSync = (value < 0.0) ? -1 : (value != 0.0);
 	else if (n == "growth_limit") r->growthLimit = value;
 	else if (n == "tline_prefetch") r->tlinePrefetch = (value != 0.0);
+	else if (n == "fmad") r->fmad = (value != 0.0);
 	else return fail("unknown option %s", name);
 	r->prepared = false;
 	return 0;
@@ -788,7 +790,7 @@ int buildJitKernel(simcu_ *r)
 {
 	JitConfig cfg;
 	cfg.threadsPerBlock = r->tpb; cfg.minBlocks = r->minBlocksUsed; cfg.gmin = r->ctl.gmin;
-	cfg.replay = r->replay; cfg.blockSync = r->blockSyncUsed; cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch;
+	cfg.replay = r->replay; cfg.blockSync = r->blockSyncUsed; cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch; cfg.fmad = r->fmad;
 	if (r->jit && r->jitProbes == r->probeRows && r->jitCfg == cfg && r->jitMeasures == r->measures)
 		return 0;
 	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows,
@@ -800,7 +802,7 @@ int buildJitKernel(simcu_ *r)
 	else {
 		std::shared_ptr<JitKernel> k(new JitKernel());
 		std::string err;
-		if (!jitCompile(src, *k, err)) return fail("%s", err.c_str());
+		if (!jitCompile(src, *k, err, cfg.fmad != 0)) return fail("%s", err.c_str());
 		if (!jitLoad(*k, r->tpb, err)) return fail("%s", err.c_str());
 		/* bounded: drop entries no handle uses any more, oldest key first */
 		for (it = gKernelCache.begin(); it != gKernelCache.end() && gKernelCache.size() >= kKernelCacheMax;) {

@@ -20,12 +20,13 @@ struct JitConfig {
 	int replay = 0;           /* 1: replay an attempt log instead of own step control (tests) */
 	int blockSync = 0;        /* 1: the warps of a block start every attempt together */
 	double growthLimit = 1e6; /* LU multipliers above this are counted (pivot growth guard; <= 0: off) */
-	int tlinePrefetch = 1;    /* circuits with >= 2 T-lines: locate + prefetch pass before the step */
+	int tlinePrefetch = 0;    /* circuits with >= 2 T-lines: locate + prefetch pass before the step */
+	int fmad = 1;             /* 0: no a*b+c contraction (the oracle's arithmetic, for the replay tests) */
 	bool operator==(const JitConfig &o) const
 	{
 		return threadsPerBlock == o.threadsPerBlock && minBlocks == o.minBlocks && gmin == o.gmin &&
 			replay == o.replay && blockSync == o.blockSync && growthLimit == o.growthLimit &&
-			tlinePrefetch == o.tlinePrefetch;
+			tlinePrefetch == o.tlinePrefetch && fmad == o.fmad;
 	}
 };
 
@@ -56,7 +57,7 @@ struct JitKernel {
 /* Returns false and fills err on failure.  If the environment variable
  * SIMCU_JIT_DUMP names a directory, the translation unit is also written there
  * (and compiled under that path, so profilers can show the source). */
-bool jitCompile(const std::string &source, JitKernel &k, std::string &err);
+bool jitCompile(const std::string &source, JitKernel &k, std::string &err, bool fmad = true);
 bool jitLoad(JitKernel &k, int threadsPerBlock, std::string &err);
 /* where libnvrtc was found ("" before the first compile) */
 const char *jitNvrtcPath();

@@ -278,14 +278,16 @@ DEVFN int cbAngleBreak(double dy0, double dx0, double dy1, double dx1, double ma
 	return (fabs(simcuAtan2(dy0, dx0) - simcuAtan2(dy1, dx1)) > maxAngle) ? 1 : 0;
 }
 
-/* state (9 doubles): x0 x1 dt0 | t0 t1 dt1 | dx0 dx1 - ; 0 = the slot of the
- * current time point, 1 = the one before (the reference's third ring slot is
- * never read) */
+/* state (6 live doubles of the 9 slots): x0 x1 - | t0 t1 dt1 | - dx1 - ; 0 = the
+ * slot of the current time point, 1 = the one before (the reference's third
+ * ring slot is never read).  (dx1, dt1) are the arguments of the PREVIOUS point's
+ * angle; they are taken over when the ring advances - x0 - x1 and t0 - t1 are
+ * then exactly what the last evaluation of that point used. */
 DEV void cbInitialize(const Inst &c, int sb, int ib, double ic)
 {
-	c.S(sb) = ic; c.S(sb + 1) = ic; c.S(sb + 2) = 0.0;
+	c.S(sb) = ic; c.S(sb + 1) = ic;
 	c.S(sb + 3) = 0.0; c.S(sb + 4) = 0.0; c.S(sb + 5) = 0.0;
-	c.S(sb + 6) = 0.0; c.S(sb + 7) = 0.0;
+	c.S(sb + 7) = 0.0;
 	c.IS(ib) = 0;
 }
 
@@ -294,20 +296,18 @@ DEV int cbIsBreak(const Inst &c, int sb, int ib, double x, double maxAngle)
 	int n = c.IS(ib);
 	if (c.time > c.S(sb + 3)) {
 		n++; c.IS(ib) = n;
-		c.S(sb + 1) = c.S(sb);               /* x */
-		c.S(sb + 4) = c.S(sb + 3);           /* t */
-		c.S(sb + 7) = c.S(sb + 6);           /* arguments of theta */
-		c.S(sb + 5) = c.S(sb + 2);
+		c.S(sb + 7) = c.S(sb) - c.S(sb + 1);         /* arguments of theta[p] */
+		c.S(sb + 5) = c.S(sb + 3) - c.S(sb + 4);
+		c.S(sb + 1) = c.S(sb);                       /* x */
+		c.S(sb + 4) = c.S(sb + 3);                   /* t */
 	}
-	/* (n - 1) % 3 < 0 only while the counter is still 0: then p = slot 0 = k */
-	const bool prev = (n >= 1);
 	c.S(sb) = x;
 	c.S(sb + 3) = c.time;
-	const double xp = prev ? c.S(sb + 1) : x, tp = prev ? c.S(sb + 4) : c.time;
-	const double dy = x - xp, dt = c.time - tp;
-	c.S(sb + 6) = dy; c.S(sb + 2) = dt;
-	const double dyp = prev ? c.S(sb + 7) : dy, dtp = prev ? c.S(sb + 5) : dt;
-	return cbAngleBreak(dy, dt, dyp, dtp, maxAngle);
+	/* (n - 1) % 3 < 0 only while the counter is still 0 (never in a transient
+	 * attempt, time > 0): then p = slot 0 = k and both angles are atan2(0, 0) */
+	if (n < 1) return 0;
+	const double dy = x - c.S(sb + 1), dt = c.time - c.S(sb + 4);
+	return cbAngleBreak(dy, dt, c.S(sb + 7), c.S(sb + 5), maxAngle);
 }
 #else
 DEV void cbInitialize(const Inst &c, int sb, int ib, double ic)

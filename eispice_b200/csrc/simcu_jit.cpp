@@ -96,7 +96,7 @@ JitKernel::~JitKernel()
 	if (library) cudaLibraryUnload((cudaLibrary_t)library);
 }
 
-bool jitCompile(const std::string &source, JitKernel &k, std::string &err)
+bool jitCompile(const std::string &source, JitKernel &k, std::string &err, bool fmad)
 {
 	if (!openNvrtc(err)) return false;
 	std::string name = "simcu_topology.cu";
@@ -110,7 +110,7 @@ bool jitCompile(const std::string &source, JitKernel &k, std::string &err)
 	nvrtcResult rc = gNvrtc.createProgram(&prog, source.c_str(), name.c_str(), 0, nullptr, nullptr);
 	if (rc != NVRTC_SUCCESS) { err = gNvrtc.errorString(rc); return false; }
 	std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
-		"--fmad=true"};
+		fmad ? "--fmad=true" : "--fmad=false"};
 	rc = gNvrtc.compileProgram(prog, (int)opts.size(), opts.data());
 	size_t logSize = 0;
 	gNvrtc.getLogSize(prog, &logSize);

@@ -145,6 +145,9 @@ int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
  * once, 0 = whole warps start together), block_sync (1: the warps of a block
  * start every attempt together and share instruction-cache lines),
  * growth_limit (LU multiplier magnitude counted as pivot growth, default 1e6),
+ * tline_prefetch (1: extra locate + L2 prefetch pass over the T-lines; measured
+ * slower, off), fmad (0: compile the kernel without a*b+c contraction - the
+ * CPU oracle's arithmetic - for the replay tests; default 1),
  * replay (see simcuSetReplayLog);
  * r = NULL: quiet (0/1) */
 int simcuSetOption(simcu_ *r, char *name, double value);

@@ -75,3 +75,23 @@ def spice_ratio(a, ref, names, current_floor=0.0):
         scale = np.where(isI, np.maximum(scale, current_floor * scale[isI].max()), scale)
     tol = parity.RELTOL * scale + np.where(isI, parity.ABSTOL, parity.VNTOL)
     return float((np.abs(a - ref) / tol).max())
+
+
+def probes_on_grid(args):
+    """Probe waveforms of one sweep instance on a given time grid:
+    (cfg, M, index, kind 'oracle' | 'ref', probes, grid) -> [ngrid, nprobes] or
+    None if that engine aborts on the instance."""
+    cfg, M, idx, kind, probes, grid = args
+    import backends
+    import parity
+    w = _workload(cfg, M)
+    nl, s = w.instance_netlist(idx)
+    try:
+        if kind == "ref":
+            d, names = backends.RefSim(nl, s).tran(w.tstep, w.tstop)
+        else:
+            d, names = backends.OracleSim(nl, s).tran(w.tstep, w.tstop)
+    except RuntimeError:
+        return None
+    d = parity.drop_degenerate(d, w.tstep)
+    return np.stack([np.interp(grid, d[:, 0], d[:, names.index(p)]) for p in probes], axis=1)

@@ -85,6 +85,7 @@ def main():
     logs = [(logged[j][1], logged[j][2], logged[j][3]) if logged[j] is not None
             else (np.zeros(0), np.zeros(0, np.int32), np.zeros(0, np.int32)) for j in range(n)]
     eng.set_replay_log(logs)
+    eng.set_option("fmad", float(os.environ.get("EXPLORE_FMAD", "0")))
     t0 = time.time()
     res2 = eng.tran_batch(w.tstep, w.tstop, 0.0, sub, w.probes, raw_max_points=cap, raw_count=n)
     rep["gpu_replay_s"] = time.time() - t0
