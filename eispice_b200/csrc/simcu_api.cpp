@@ -960,7 +960,7 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		 *  - a full machine: the warps of a block start every attempt together
 		 *    (block_sync) and share instruction-cache lines - one block per SM;
 		 *  - a working set far beyond the register file (cfg5: 763 doubles per
-		 *    instance) gains more from 32 resident warps at 64 registers than from
+		 *    instance) gains more from 28 resident warps at 72 registers than from
 		 *    255 registers at 8 warps; mid-size circuits (cfg4: 434) the opposite;
 		 *  - small circuits (N <= 12) in big batches: 128 registers, 16 warps. */
 		const int workingSet = p.stateDoubles + p.nnzA + 3 * p.N + (int)p.pmap.size();
@@ -971,7 +971,7 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 			r->tpb = std::min(1024, std::max(32, (r->tpbOpt / 32) * 32));
 			if (sync < 0) sync = 0;
 		} else if (full && p.N > 12) {
-			r->tpb = (workingSet >= 600) ? 1024 : 256;
+			r->tpb = (workingSet >= 600) ? 896 : 256;
 			if (sync < 0) sync = 1;
 		} else {
 			r->tpb = 64;

@@ -368,6 +368,8 @@ def superlu_sequences(netlist, vi_set, tstep, tstop, max_records=100000):
     lib.ref_probe_capture(max_records)
     try:
         sim.tran(tstep, tstop)
+    except RuntimeError:
+        pass          # the reference aborted; what it factorised until then was captured
     finally:
         n = C.c_int(0)
         cnt = lib.ref_probe_count(C.byref(n))
