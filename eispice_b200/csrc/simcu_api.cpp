@@ -1455,6 +1455,7 @@ int simcuRunOperatingPoint(simcu_ *r, int instance, double *data[], char **varia
 }
 
 /* ---- introspection (host only) --------------------------------------------- */
+const char *simcuNvrtcPath(void) { return jitNvrtcPath(); }
 int simcuNumUnknowns(simcu_ *r) { return r ? (int)r->nl.rowName.size() - 1 : -1; }
 int simcuNumNonzeros(simcu_ *r) { return r ? (int)r->nl.nodes.size() : -1; }
 

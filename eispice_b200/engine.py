@@ -122,6 +122,7 @@ def lib():
     L.simcuFree.argtypes = [vp]
     L.simcuCompileOnly.argtypes = [vp, vp, C.c_int, vp, ip]
     L.simcuSetDevice.argtypes = [C.c_int]
+    L.simcuNvrtcPath.restype = cp
     L.simcuTransposeOutput.argtypes = [vp, vp, vp, vp, ip, ip]
     L.simcuCommUniqueId.argtypes = [vp, C.c_int]
     L.simcuCommInit.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
@@ -133,6 +134,11 @@ def lib():
 
 def _b(s):
     return str(s).encode()
+
+
+def nvrtc_path():
+    """Path and version of the NVRTC library in use ("" before the first compile)."""
+    return lib().simcuNvrtcPath().decode()
 
 
 def set_device(index):
@@ -494,10 +500,12 @@ class Engine:
         batch walks into a collapse of the step size that another pivot order does
         not (the reference has the same disease: its own order aborts every
         typ/falling instance of cfg5).  Those instances run again as a small batch
-        of their own - pilots chosen among themselves, a stricter pivot threshold,
-        a history ring as deep as memory allows.  Returns the number rescued."""
+        of their own - pilots chosen among themselves, the reference's arithmetic
+        (no a*b+c contraction: measured to cure instances that three pivot
+        sequences did not), then also a stricter pivot threshold, with a history
+        ring as deep as memory allows.  Returns the number rescued."""
         rescued = 0
-        for threshold in (0.5, 0.9):
+        for threshold in (None, 0.9):
             bad = np.nonzero((status == 1) | (status == 5) | (status == 6))[0]
             if len(bad) == 0 or len(bad) > 64 + self.num_instances // 100:
                 break
@@ -507,7 +515,9 @@ class Engine:
                     if k not in ("raw_max_points", "raw_first", "raw_count", "replay", "threads_per_block",
                                  "block_sync", "hist_records"):
                         sub.set_option(k, v)
-                sub.set_option("pivot_threshold", threshold)
+                if threshold is not None:
+                    sub.set_option("pivot_threshold", threshold)
+                sub.set_option("fmad", 0)
                 sub.set_option("history_retry", 1)
                 sub.set_params({k: v[bad] for k, v in self._params.items()})
                 if measures is not None:

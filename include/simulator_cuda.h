@@ -283,6 +283,10 @@ int simcuFetchRaw(simcu_ *r, int instance, double *data[], int *numPoints,
 int simcuFetchRawBlock(simcu_ *r, double *out, int *numPoints);
 
 /* ---- introspection (host only, no GPU needed) ----------------------------- */
+/* path and version of the NVRTC library the kernels were compiled with ("" before
+ * the first compile).  The toolkit's own copy is preferred over one a host
+ * application (PyTorch) has already loaded; override with SIMCU_NVRTC. */
+const char *simcuNvrtcPath(void);
 int simcuNumUnknowns(simcu_ *r);
 int simcuNumNonzeros(simcu_ *r);
 /* CSC pattern in the reference's order (core/node.c:56-66, matrix.c:476-497) */

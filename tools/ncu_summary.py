@@ -30,7 +30,14 @@ with open(raw_csv, "w") as f:
     for h in hdr:
         if h in m and not h.startswith("ID"):
             w.writerow([h, m[h][1], m[h][0]])
-dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+if "dram__bytes_read.sum" in m:
+    dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+    how = "dram__bytes_read.sum + dram__bytes_write.sum"
+else:      # captures without the memory section: average rate x duration
+    rate = float(m["dram__bytes.sum.per_second"][0]) * {"Gbyte/s": 1e9, "Tbyte/s": 1e12, "Mbyte/s": 1e6}[m["dram__bytes.sum.per_second"][1]]
+    dur = float(m["gpu__time_duration.sum"][0]) * {"s": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9}[m["gpu__time_duration.sum"][1]]
+    dram = rate * dur
+    how = "dram__bytes.sum.per_second x gpu__time_duration.sum"
 inst = num("smsp__inst_executed.sum")
 path = os.path.join(ROOT, "profiles", "summary.json")
 summ = json.load(open(path)) if os.path.exists(path) else {}
@@ -39,8 +46,8 @@ summ[key] = {
     "warp_instructions_per_launch": inst,
     "accepted_instance_timesteps_per_launch": accepted,
     "warp_instructions_per_instance_timestep": inst / accepted,
-    "source": "profiles/%s_raw.csv (ncu, dram__bytes_read.sum + dram__bytes_write.sum and "
-              "smsp__inst_executed.sum, one launch of simcuJitKernel)" % name,
+    "source": "profiles/%s_raw.csv (ncu, %s and smsp__inst_executed.sum, one launch of "
+              "simcuJitKernel)" % (name, how),
 }
 json.dump(summ, open(path, "w"), indent=1)
 print(json.dumps(summ[key], indent=1))
