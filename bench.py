@@ -453,11 +453,12 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
             "clocks": clocks,
         }
-        # measured DRAM traffic and issued warp instructions of the dominant kernel, per
-        # launch, from the committed ncu capture of this same workload
-        # (profiles/summary.json), else null.  The kernel keeps its state on chip, so
-        # HBM is not what bounds it: issue_frac = warp instructions per second /
-        # (SMs x 4 schedulers x SM clock) is the bound that explains `value`.
+        # measured DRAM traffic of the dominant kernel, per launch, from the committed
+        # ncu capture of this same workload (profiles/summary.json), else null; next
+        # to it dram_frac = measured DRAM bytes/s / measured HBM peak and issue_frac =
+        # issue slots used / available (148 SMs x 4 schedulers), both from that
+        # capture: what actually bounds the kernel is the latency of its thread-local
+        # state streaming through L2/HBM, not the algorithmic byte model.
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "summary.json")))
             ent = prof.get("%s@%d" % (name, w.M))
@@ -469,6 +470,11 @@ def main():
                     mhz = (clocks or {}).get("sm_mhz") or 1965.0
                     line["roofline"]["issue_frac"] = ipt * (value / world) / (148 * 4 * mhz * 1e6)
                     line["roofline"]["warp_instructions_per_instance_timestep"] = ipt
+                elif ent.get("issue_active_frac"):
+                    # measured directly by ncu on that capture (sm__issue_active)
+                    line["roofline"]["issue_frac"] = ent["issue_active_frac"]
+                if ent.get("dram_throughput_frac_of_measured_peak"):
+                    line["roofline"]["dram_frac"] = ent["dram_throughput_frac_of_measured_peak"]
         except (OSError, ValueError, KeyError):
             pass
         if world == 1 and not a.no_extras:

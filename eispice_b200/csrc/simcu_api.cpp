@@ -117,7 +117,7 @@ struct _simcu {
 	int blockSyncUsed = 0;
 	double growthLimit = 1e6;       /* LU multiplier magnitude that counts as pivot growth */
 	int tlinePrefetch = 0;          /* locate + prefetch pass over the T-lines (>= 2 lines): measured slower */
-	int fmad = 1;                   /* 0: compile without a*b+c contraction (replay tests) */
+	int fmad = 0;                   /* 0: no a*b+c contraction - the reference's arithmetic (default) */
 	std::vector<int> replayOff, replayFlag, replayLinOff, replayLin;
 	std::vector<double> replayTime;
 	std::vector<char> active[2];

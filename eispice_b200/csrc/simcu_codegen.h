@@ -21,7 +21,7 @@ struct JitConfig {
 	int blockSync = 0;        /* 1: the warps of a block start every attempt together */
 	double growthLimit = 1e6; /* LU multipliers above this are counted (pivot growth guard; <= 0: off) */
 	int tlinePrefetch = 0;    /* circuits with >= 2 T-lines: locate + prefetch pass before the step */
-	int fmad = 1;             /* 0: no a*b+c contraction (the oracle's arithmetic, for the replay tests) */
+	int fmad = 0;             /* 0: no a*b+c contraction: the reference's (and the oracle's) arithmetic */
 	bool operator==(const JitConfig &o) const
 	{
 		return threadsPerBlock == o.threadsPerBlock && minBlocks == o.minBlocks && gmin == o.gmin &&

@@ -23,6 +23,22 @@ DEV double simcuAtan2(double y, double x) { return (y == 0.0 && x > 0.0) ? y : s
 DEVFN double simcuExp(double x) { return exp(x); }
 
 #define MaxAbs(x, y) ((fabs(x) > fabs(y)) ? fabs(x) : fabs(y))
+/* Products and sums that must NOT be contracted into a*b+c.  The companion
+ * models and the LTE estimate rely on exact cancellation: for a capacitor at
+ * rest C*x(n+1) - C*x(n) is exactly 0 in the reference's arithmetic, so its
+ * divided differences vanish and the step grows; a fused multiply-add keeps the
+ * rounding error of one product (1e-16 q), the third divided difference turns
+ * it into 1e-16 q / h^3, and the smaller the step the larger the spurious error
+ * estimate - the step size collapses and never recovers (measured: cfg4 instance
+ * 52883 of the 262 144 sweep, 32 786 accepted steps into a history overflow with
+ * contraction, 3 739 steps to the end without). */
+#ifdef __CUDA_ARCH__
+#define MUL_RN(a, b) __dmul_rn((a), (b))
+#define ADD_RN(a, b) __dadd_rn((a), (b))
+#else
+#define MUL_RN(a, b) ((a) * (b))
+#define ADD_RN(a, b) ((a) + (b))
+#endif
 #define Min3(x, y, z) ((x < y) ? ((z < x) ? z : x) : ((z < y) ? z : y))
 
 #ifdef SIMCU_JIT
@@ -437,7 +453,7 @@ DEV void itIntegrate(Inst &c, int sb, int ib, double x0, double ydtdx,
 	}
 	const double h = c.itH[0];
 	AGE(c, sb, RX, 0) = x0;
-	const double yn = c.S(sb + 1) * x0 - c.S(sb);
+	const double yn = ADD_RN(MUL_RN(c.S(sb + 1), x0), -c.S(sb));
 	AGE(c, sb, RY, 0) = yn;
 	AGE(c, sb, RF, 0) = ydtdx;
 	const double fp = AGEQ(c, sb, RF, 1, nn);
@@ -448,7 +464,7 @@ DEV void itIntegrate(Inst &c, int sb, int ib, double x0, double ydtdx,
 		dydx0 = 2.0 * ydtdx / h;
 		double mult = ydtdx / fp;
 		if (isnan(mult)) mult = 1 / c.a.ctl.gmin;
-		y0 = dydx0 * x0 + mult * yn;
+		y0 = ADD_RN(MUL_RN(dydx0, x0), MUL_RN(mult, yn));
 	}
 	c.S(sb + 1) = dydx0;
 	c.S(sb) = y0;
@@ -459,17 +475,18 @@ DEVFN double itNextStepFn(int order, double reltol, double chgtol, double trtol,
 		double x0, double ydtdx, double ieq, double g, double ry0, double hn, double xn, double fn,
 		double f1, double x1, double h1, double f2, double x2, double h2)
 {
-	const double y0 = g * x0 - ieq;
-	const double ey = reltol * MaxAbs(ry0, y0) + abstol;
-	const double eyp = reltol * MaxAbs(MaxAbs(x0, xn) * (ydtdx / hn), chgtol);
+	const double y0 = ADD_RN(MUL_RN(g, x0), -ieq);
+	const double ey = ADD_RN(MUL_RN(reltol, MaxAbs(ry0, y0)), abstol);
+	const double eyp = MUL_RN(reltol, MaxAbs(MUL_RN(MaxAbs(x0, xn), (ydtdx / hn)), chgtol));
 	const double e = MaxAbs(eyp, ey);
+	const double q0 = MUL_RN(ydtdx, x0), qn = MUL_RN(fn, xn), q1 = MUL_RN(f1, x1);
 	double h, dd;
 	if (order < 2) {
-		dd = DD2((ydtdx * x0), (fn * xn), (f1 * x1), hn, h1);
+		dd = DD2(q0, qn, q1, hn, h1);
 		dd *= 1.0 / 2.0;
 		h = trtol * e / MaxAbs(dd, abstol);
 	} else {
-		dd = DD3((ydtdx * x0), (fn * xn), (f1 * x1), (f2 * x2), hn, h1, h2);
+		dd = DD3(q0, qn, q1, MUL_RN(f2, x2), hn, h1, h2);
 		dd *= 1.0 / 12.0;
 		h = sqrtf(trtol * e / MaxAbs(dd, abstol));
 	}
@@ -518,7 +535,7 @@ DEV void itIntegrate(Inst &c, int sb, int ib, double x0, double ydtdx,
 	RING(c, sb, RH, n) = h;
 	RING(c, sb, RT, (nn + 1) % 4) = t0;
 	RING(c, sb, RX, n) = x0;
-	const double yn = c.D(sb + 1) * x0 - c.D(sb);
+	const double yn = ADD_RN(MUL_RN(c.D(sb + 1), x0), -c.D(sb));
 	RING(c, sb, RY, n) = yn;
 	RING(c, sb, RF, n) = ydtdx;
 	if (c.order < 2) {
@@ -528,7 +545,7 @@ DEV void itIntegrate(Inst &c, int sb, int ib, double x0, double ydtdx,
 		dydx0 = 2.0 * ydtdx / h;
 		double mult = ydtdx / RING(c, sb, RF, p);
 		if (isnan(mult)) mult = 1 / c.a.ctl.gmin;
-		y0 = dydx0 * x0 + mult * yn;
+		y0 = ADD_RN(MUL_RN(dydx0, x0), MUL_RN(mult, yn));
 	}
 	c.D(sb + 1) = dydx0;
 	c.D(sb) = y0;
@@ -541,21 +558,20 @@ DEV double itNextStep(Inst &c, int sb, int ib, double x0, double ydtdx, double a
 	const SimcuControl &k = c.a.ctl;
 	const int nn = c.IS(ib);
 	const int n = nn % 4, p1 = (nn - 1) % 4, p2 = (nn - 2) % 4;
-	const double y0 = c.D(sb + 1) * x0 - c.D(sb);
-	const double ey = k.reltol * MaxAbs(RING(c, sb, RY, n), y0) + abstol;
+	const double y0 = ADD_RN(MUL_RN(c.D(sb + 1), x0), -c.D(sb));
+	const double ey = ADD_RN(MUL_RN(k.reltol, MaxAbs(RING(c, sb, RY, n), y0)), abstol);
 	const double hn = RING(c, sb, RH, n), xn = RING(c, sb, RX, n);
-	const double eyp = k.reltol * MaxAbs(MaxAbs(x0, xn) * (ydtdx / hn), k.chgtol);
+	const double eyp = MUL_RN(k.reltol, MaxAbs(MUL_RN(MaxAbs(x0, xn), (ydtdx / hn)), k.chgtol));
 	const double e = MaxAbs(eyp, ey);
+	const double q0 = MUL_RN(ydtdx, x0), qn = MUL_RN(RING(c, sb, RF, n), xn);
+	const double q1 = MUL_RN(RING(c, sb, RF, p1), RING(c, sb, RX, p1));
 	double h, dd;
 	if (c.order < 2) {
-		dd = DD2((ydtdx * x0), (RING(c, sb, RF, n) * xn),
-				(RING(c, sb, RF, p1) * RING(c, sb, RX, p1)), hn, RING(c, sb, RH, p1));
+		dd = DD2(q0, qn, q1, hn, RING(c, sb, RH, p1));
 		dd *= 1.0 / 2.0;
 		h = k.trtol * e / MaxAbs(dd, abstol);
 	} else {
-		dd = DD3((ydtdx * x0), (RING(c, sb, RF, n) * xn),
-				(RING(c, sb, RF, p1) * RING(c, sb, RX, p1)),
-				(RING(c, sb, RF, p2) * RING(c, sb, RX, p2)),
+		dd = DD3(q0, qn, q1, MUL_RN(RING(c, sb, RF, p2), RING(c, sb, RX, p2)),
 				hn, RING(c, sb, RH, p1), RING(c, sb, RH, p2));
 		dd *= 1.0 / 12.0;
 		h = sqrtf(k.trtol * e / MaxAbs(dd, abstol));

@@ -500,12 +500,11 @@ class Engine:
         batch walks into a collapse of the step size that another pivot order does
         not (the reference has the same disease: its own order aborts every
         typ/falling instance of cfg5).  Those instances run again as a small batch
-        of their own - pilots chosen among themselves, the reference's arithmetic
-        (no a*b+c contraction: measured to cure instances that three pivot
-        sequences did not), then also a stricter pivot threshold, with a history
-        ring as deep as memory allows.  Returns the number rescued."""
+        of their own - pilots chosen among themselves (another pivot sequence), then
+        a stricter pivot threshold, then the other rounding (a*b+c contraction on),
+        with a history ring as deep as memory allows.  Returns the number rescued."""
         rescued = 0
-        for threshold in (None, 0.9):
+        for threshold, fmad in ((None, 0), (0.9, 0), (None, 1)):
             bad = np.nonzero((status == 1) | (status == 5) | (status == 6))[0]
             if len(bad) == 0 or len(bad) > 64 + self.num_instances // 100:
                 break
@@ -513,11 +512,11 @@ class Engine:
             try:
                 for k, v in self._options.items():
                     if k not in ("raw_max_points", "raw_first", "raw_count", "replay", "threads_per_block",
-                                 "block_sync", "hist_records"):
+                                 "block_sync", "hist_records", "fmad", "pivot_threshold"):
                         sub.set_option(k, v)
                 if threshold is not None:
                     sub.set_option("pivot_threshold", threshold)
-                sub.set_option("fmad", 0)
+                sub.set_option("fmad", fmad)
                 sub.set_option("history_retry", 1)
                 sub.set_params({k: v[bad] for k, v in self._params.items()})
                 if measures is not None:

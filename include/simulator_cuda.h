@@ -146,8 +146,11 @@ int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
  * start every attempt together and share instruction-cache lines),
  * growth_limit (LU multiplier magnitude counted as pivot growth, default 1e6),
  * tline_prefetch (1: extra locate + L2 prefetch pass over the T-lines; measured
- * slower, off), fmad (0: compile the kernel without a*b+c contraction - the
- * CPU oracle's arithmetic - for the replay tests; default 1),
+ * slower, off), fmad (default 0: the kernel is compiled WITHOUT a*b+c
+ * contraction, i.e. with the reference's arithmetic - under the same pivot
+ * sequence it then reproduces the reference algorithm bit for bit wherever no
+ * libm function is involved; 1 allows contraction: 0-3 % faster, results differ
+ * in the last bits and step sequences may differ),
  * replay (see simcuSetReplayLog);
  * r = NULL: quiet (0/1) */
 int simcuSetOption(simcu_ *r, char *name, double value);

@@ -586,3 +586,35 @@ def test_run_transient_batch_one_call_entry():
     assert d.shape[0] > 500
     one.close()
     eng2.close()
+
+
+@pytest.mark.parametrize("cfg,M", [("cfg1", 64), ("cfg4", 48)])
+def test_adaptive_run_is_bit_identical_to_the_oracle_under_the_same_pivots(cfg, M):
+    """The production kernel is compiled without a*b+c contraction (option fmad,
+    default 0), i.e. with the reference's arithmetic.  Where no libm function is
+    involved (cfg1: pulse + R + C; cfg4: IBIS tables + lossless T-line) the
+    ADAPTIVE run - the engine's own step control, no replay - then equals the
+    oracle under the same pivot sequence bit for bit: same accepted times, same
+    values of every unknown at every step."""
+    w = workloads.make(cfg, M)
+    eng = engine.Engine(w.cct.netlist(), w.M)
+    res = eng.tran_batch(w.tstep, w.tstop, 0.0, w.params, w.probes, raw_max_points=16000,
+                         raw_count=w.M)
+    raws = eng.fetch_raw_all(16000)
+    piv = eng.pivots(0) + eng.pivots(1)
+    identical = 0
+    for i in range(w.M):
+        nl, s = w.instance_netlist(i)
+        ora = backends.OracleSim(nl, s)
+        ora.set_pivots(0, piv[0], piv[1])
+        ora.set_pivots(1, piv[2], piv[3])
+        try:
+            od, _ = ora.tran(w.tstep, w.tstop)
+        except RuntimeError:
+            assert res.status[i] != 0, "oracle aborts on %d, the engine does not" % i
+            identical += 1
+            continue
+        assert res.status[i] == 0
+        identical += int(raws[i].shape == od.shape and np.array_equal(raws[i], od))
+    assert identical == w.M, "%d of %d instances bit-identical" % (identical, w.M)
+    eng.close()
