@@ -136,7 +136,7 @@ struct _simcu {
 		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
 		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2, dMeasure, dMeasureLevel,
 		dReplayOff, dReplayTime, dReplayFlag, dReplayLinOff, dReplayLin;
-	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dOutRaw, dWs, dRemaining;
+	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dStatusT, dOutRaw, dWs, dRemaining;
 	int *hRemaining = nullptr;      /* pinned */
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 	std::vector<char *> variableNames;
@@ -156,7 +156,7 @@ struct _simcu {
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
 			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder, &dOrder2, &dMeasure,
 			&dMeasureLevel, &dReplayOff, &dReplayTime, &dReplayFlag, &dReplayLinOff, &dReplayLin, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
-			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dOutRaw,
+			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dStatusT, &dOutRaw,
 			&dWs, &dRemaining};
 		for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) all[i]->release();
 		if (hRemaining) cudaFreeHost(hRemaining);
@@ -1283,7 +1283,13 @@ int simcuTransposeOutput(simcu_ *r, void *stream, void **deviceData, void **devi
 			return fail("transpose kernel launch failed");
 	}
 	if (deviceData) *deviceData = rows > 0 ? r->dOutT.p : nullptr;
-	if (deviceStatus) *deviceStatus = r->dCI.as<int>() + (size_t)CI_STATUS * M;
+	if (deviceStatus) {
+		/* a snapshot: the next batch may already be running when this one travels */
+		if (r->dStatusT.reserve((size_t)M * 4)) return -1;
+		CU(cudaMemcpyAsync(r->dStatusT.p, r->dCI.as<int>() + (size_t)CI_STATUS * M, (size_t)M * 4,
+				cudaMemcpyDeviceToDevice, st));
+		*deviceStatus = r->dStatusT.p;
+	}
 	if (numInstances) *numInstances = M;
 	if (valuesPerInstance) *valuesPerInstance = rows;
 	return 0;

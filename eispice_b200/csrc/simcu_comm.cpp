@@ -94,6 +94,13 @@ struct _simcuComm {
 	int *hStatus = nullptr;       /* root, pinned: [nranks][M] */
 	size_t hStatusBytes = 0;
 	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+	cudaEvent_t evReady = nullptr;   /* compute stream: the transposed block is complete */
+	cudaStream_t side = nullptr;     /* NCCL + copies run here, beside the next batch */
+	/* the gather in flight (simcuGatherOutputAsync ... simcuGatherWait) */
+	bool pending = false, pendingRoot = false;
+	int pendingM = 0;
+	int *pendingStatus = nullptr;
+	long long pendingNccl = 0, pendingCopy = 0;
 };
 
 extern "C" {
@@ -127,6 +134,8 @@ int simcuCommInit(simcuComm_ **out, int nranks, int rank, const char *id, int by
 	ncclResult_t rc = gNccl.commInitRank(&c->comm, nranks, u, rank);
 	if (rc != ncclSuccess) { delete c; return commFail("ncclCommInitRank", gNccl.errorString(rc)); }
 	for (int i = 0; i < 3; i++) cudaEventCreate(&c->ev[i]);
+	cudaEventCreateWithFlags(&c->evReady, cudaEventDisableTiming);
+	cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
 	*out = c;
 	return 0;
 }
@@ -137,21 +146,28 @@ int simcuCommDestroy(simcuComm_ **c)
 	if ((*c)->dGather) cudaFree((*c)->dGather);
 	if ((*c)->hStatus) cudaFreeHost((*c)->hStatus);
 	for (int i = 0; i < 3; i++) if ((*c)->ev[i]) cudaEventDestroy((*c)->ev[i]);
+	if ((*c)->evReady) cudaEventDestroy((*c)->evReady);
+	if ((*c)->side) cudaStreamDestroy((*c)->side);
 	if ((*c)->comm) gNccl.commDestroy((*c)->comm);
 	delete *c;
 	*c = nullptr;
 	return 0;
 }
 
-int simcuGatherOutput(simcu_ *r, simcuComm_ *c, int root, double *hostData, int *hostStatus,
-		void *stream, simcuGatherStats_ *stats)
+int simcuGatherOutputAsync(simcu_ *r, simcuComm_ *c, int root, double *hostData, int *hostStatus,
+		void *stream)
 {
 	if (!r || !c || root < 0 || root >= c->nranks) return commFail("simcuGatherOutput", "bad arguments");
-	cudaStream_t st = (cudaStream_t)stream;
+	if (c->pending) return commFail("simcuGatherOutputAsync", "the previous gather has not been waited for");
+	cudaStream_t st = c->side;
 	int M = 0, rows = 0;
 	const double *block = nullptr;
 	const int *status = nullptr;
+	/* transpose on the caller's (compute) stream; everything after it runs on the
+	 * side stream, so the caller can launch its next batch at once */
 	if (simcuTransposeOutput(r, stream, (void **)&block, (void **)&status, &M, &rows)) return -1;
+	CUC(cudaEventRecord(c->evReady, (cudaStream_t)stream));
+	CUC(cudaStreamWaitEvent(c->side, c->evReady, 0));
 	const size_t count = (size_t)M * rows, blockBytes = count * 8;
 	const int W = c->nranks;
 	const bool isRoot = (c->rank == root);
@@ -206,20 +222,40 @@ int simcuGatherOutput(simcu_ *r, simcuComm_ *c, int root, double *hostData, int 
 		}
 	}
 	CUC(cudaEventRecord(c->ev[2], st));
-	CUC(cudaStreamSynchronize(st));
-	if (isRoot && hostStatus)
+	c->pending = true; c->pendingRoot = isRoot; c->pendingM = M;
+	c->pendingStatus = isRoot ? hostStatus : nullptr;
+	c->pendingNccl = isRoot ? (long long)(blockBytes + (size_t)M * 4) * (W - 1)
+		: (W > 1 ? (long long)(blockBytes + (size_t)M * 4) : 0);
+	c->pendingCopy = isRoot ? (long long)(blockBytes + (size_t)M * 4) * W : 0;
+	return 0;
+}
+
+int simcuGatherWait(simcuComm_ *c, simcuGatherStats_ *stats)
+{
+	if (!c) return -1;
+	if (!c->pending) return 0;
+	CUC(cudaEventSynchronize(c->ev[2]));
+	c->pending = false;
+	const int W = c->nranks, M = c->pendingM;
+	if (c->pendingRoot && c->pendingStatus)
 		for (int p = 0; p < W; p++)
-			for (int i = 0; i < M; i++) hostStatus[(size_t)i * W + p] = c->hStatus[(size_t)M * p + i];
+			for (int i = 0; i < M; i++) c->pendingStatus[(size_t)i * W + p] = c->hStatus[(size_t)M * p + i];
 	if (stats) {
 		float a = 0.f, b = 0.f;
 		cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
 		cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
 		stats->ncclMs = a; stats->copyMs = b;
-		stats->ncclBytes = isRoot ? (long long)(blockBytes + (size_t)M * 4) * (W - 1)
-			: (W > 1 ? (long long)(blockBytes + (size_t)M * 4) : 0);
-		stats->copyBytes = isRoot ? (long long)(blockBytes + (size_t)M * 4) * W : 0;
+		stats->ncclBytes = c->pendingNccl;
+		stats->copyBytes = c->pendingCopy;
 	}
 	return 0;
+}
+
+int simcuGatherOutput(simcu_ *r, simcuComm_ *c, int root, double *hostData, int *hostStatus,
+		void *stream, simcuGatherStats_ *stats)
+{
+	if (simcuGatherOutputAsync(r, c, root, hostData, hostStatus, stream)) return -1;
+	return simcuGatherWait(c, stats);
 }
 
 }  /* extern "C" */

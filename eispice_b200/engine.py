@@ -128,6 +128,8 @@ def lib():
     L.simcuCommInit.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
     L.simcuCommDestroy.argtypes = [vp]
     L.simcuGatherOutput.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
+    L.simcuGatherOutputAsync.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.simcuGatherWait.argtypes = [vp, vp]
     _lib = L
     return L
 

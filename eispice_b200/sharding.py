@@ -131,6 +131,30 @@ class Gatherer:
         data, stat = eng.fetch()
         return self.gather_host(data, stat, num_instances, root)
 
+    def gather_async(self, eng, root=0, out=None, status=None):
+        """NCCL only: queue the gather of the batch `eng` has just run and return at
+        once, so the next batch can be launched while the waveforms travel.  The
+        root passes its (pinned) host arrays for W * shard_size instances; they are
+        complete after ``wait()``."""
+        if not self.nccl:
+            raise RuntimeError("gather_async needs the NCCL backend")
+        if self.rank == root:
+            rc = self.L.simcuGatherOutputAsync(eng.h, self.comm, root, out.ctypes.data,
+                                               status.ctypes.data, None)
+        else:
+            rc = self.L.simcuGatherOutputAsync(eng.h, self.comm, root, None, None, None)
+        if rc:
+            raise RuntimeError("simcuGatherOutputAsync failed")
+
+    def wait(self):
+        """Completes the gather queued by gather_async (no-op if none is pending)."""
+        from . import engine
+        st = engine.GatherStats()
+        if self.L.simcuGatherWait(self.comm, C.byref(st)):
+            raise RuntimeError("simcuGatherWait failed")
+        self.last = st.as_dict()
+        return self.last
+
     def gather_host(self, data, stat, num_instances, root=0):
         """gloo path: dist.gather of [per, ...] host blocks, interleaved on the root."""
         import torch

@@ -259,6 +259,16 @@ int simcuCommInit(simcuComm_ **c, int nranks, int rank, const char *id, int byte
 int simcuCommDestroy(simcuComm_ **c);
 int simcuGatherOutput(simcu_ *r, simcuComm_ *c, int root, double *hostData, int *hostStatus,
 		void *stream, simcuGatherStats_ *stats);
+/* The same in two halves, for callers that pipeline batches: Async transposes on
+ * `stream` (the stream of simcuRunDevice) and queues the NCCL transfer and the
+ * copies to the host on the communicator's own stream, then returns - the next
+ * simcuRunDevice can start while the waveforms of this one are still travelling
+ * (they only read buffers the next batch does not touch until ITS gather).
+ * Wait blocks until the host buffers are complete.  One gather in flight per
+ * communicator; host buffers must stay valid (and should be pinned) until Wait. */
+int simcuGatherOutputAsync(simcu_ *r, simcuComm_ *c, int root, double *hostData, int *hostStatus,
+		void *stream);
+int simcuGatherWait(simcuComm_ *c, simcuGatherStats_ *stats);
 
 /* Device-side post-processing (eispice NOTES:40 "Add post-processors"): n
  * running measures, each on one unknown probes[i] ("v(node)" / "i(refdes)"),
