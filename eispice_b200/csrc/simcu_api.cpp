@@ -115,10 +115,12 @@ struct _simcu {
 	int claimBelow = 31;            /* lane claiming policy of the specialised kernel */
 	int blockSync = -1;             /* warps of a block run their attempts in step (I-cache sharing); -1 = automatic */
 	int blockSyncUsed = 0;
+	int syncGroup = 0;              /* warps per barrier group (0 = the whole block) */
 	double growthLimit = 1e6;       /* LU multiplier magnitude that counts as pivot growth */
 	int tlinePrefetch = 0;          /* locate + prefetch pass over the T-lines (>= 2 lines): measured slower */
 	int fmad = 0;                   /* 0: no a*b+c contraction - the reference's arithmetic (default) */
 	std::vector<int> replayOff, replayFlag, replayLinOff, replayLin;
+	std::vector<double> winTstep, winTstop, winTmax;   /* per-instance analysis windows (empty: one window) */
 	std::vector<double> replayTime;
 	std::vector<char> active[2];
 	std::vector<double> consts[2];      /* per phase: literal value of a slot, NaN = varies */
@@ -135,7 +137,7 @@ struct _simcu {
 	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
 		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
 		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2, dMeasure, dMeasureLevel,
-		dReplayOff, dReplayTime, dReplayFlag, dReplayLinOff, dReplayLin;
+		dReplayOff, dReplayTime, dReplayFlag, dReplayLinOff, dReplayLin, dWin;
 	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dStatusT, dOutRaw, dWs, dRemaining;
 	int *hRemaining = nullptr;      /* pinned */
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -155,7 +157,7 @@ struct _simcu {
 	{
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
 			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder, &dOrder2, &dMeasure,
-			&dMeasureLevel, &dReplayOff, &dReplayTime, &dReplayFlag, &dReplayLinOff, &dReplayLin, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
+			&dMeasureLevel, &dReplayOff, &dReplayTime, &dReplayFlag, &dReplayLinOff, &dReplayLin, &dWin, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
 			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dStatusT, &dOutRaw,
 			&dWs, &dRemaining};
 		for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) all[i]->release();
@@ -490,11 +492,25 @@ int simcuAddVITableSet(simcu_ *r, char *refdes, double **vi, int *viLength, doub
 	return (int)d->sets.size() - 1;
 }
 
+int simcuAddSourceTableSet(simcu_ *r, char *refdes, double **table, int *length)
+{
+	if (!r || !refdes) return -1;
+	if (r->locked) return fail("Can't add a table set to a simulator that has run.");
+	Dev *d = r->nl.find(refdes);
+	if (!d || (d->kind != DK_V && d->kind != DK_I) || (d->wtype != 'l' && d->wtype != 'c'))
+		return fail("%s is not a PWL / PWC source", refdes);
+	if (!table || !*table || !length || *length < 1) return fail("source %s needs a table", refdes);
+	d->wsets.push_back(std::make_pair(table, length));
+	r->compiled = false; r->prepared = false;
+	return (int)d->wsets.size();
+}
+
 int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex, int stride)
 {
 	if (!r || !refdes || !setIndex) return -1;
 	Dev *d = r->nl.find(refdes);
-	if (!d || d->kind != DK_VI) return fail("%s is not a VI device", refdes);
+	const bool source = d && (d->kind == DK_V || d->kind == DK_I) && (d->wtype == 'l' || d->wtype == 'c');
+	if (!d || (d->kind != DK_VI && !source)) return fail("%s is not a VI device or a PWL / PWC source", refdes);
 	const bool isNew = d->instSet.empty();
 	d->instSet.resize(r->M);
 	bool changed = isNew;
@@ -540,6 +556,7 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "claim_below") r->claimBelow = std::max(0, std::min(31, (int)value));
 	else if (n == "replay") r->replay = (value != 0.0);
 	else if (n == "block_sync") r->blockSync = (value < 0.0) ? -1 : (value != 0.0);
+	else if (n == "sync_group") r->syncGroup = std::max(0, std::min(15, (int)value));
 	else if (n == "growth_limit") r->growthLimit = value;
 	else if (n == "tline_prefetch") r->tlinePrefetch = (value != 0.0);
 	else if (n == "fmad") r->fmad = (value != 0.0);
@@ -555,6 +572,24 @@ int simcuSetPivots(simcu_ *r, int phase, const int *pc, const int *pr, int n)
 	if (pc && pr) {
 		r->forcePc[phase].assign(pc, pc + n);
 		r->forcePr[phase].assign(pr, pr + n);
+	}
+	r->prepared = false;
+	return 0;
+}
+
+int simcuSetInstanceWindow(simcu_ *r, const double *tstep, const double *tstop, const double *tmax,
+		int stride)
+{
+	if (!r) return -1;
+	r->winTstep.clear(); r->winTstop.clear(); r->winTmax.clear();
+	if (tstep && tstop) {
+		for (int i = 0; i < r->M; i++) {
+			const double ts = tstep[(size_t)i * stride], te = tstop[(size_t)i * stride];
+			if (!(ts > 0.0) || !(te > 0.0)) return fail("instance %d: tstep and tstop must be positive", i);
+			double tm = tmax ? tmax[(size_t)i * stride] : 0.0;
+			if (tm == 0.0) { tm = te / 50; tm = (ts < tm) ? ts : tm; }      /* core/simulator.c:91-94 */
+			r->winTstep.push_back(ts); r->winTstop.push_back(te); r->winTmax.push_back(tm);
+		}
 	}
 	r->prepared = false;
 	return 0;
@@ -790,7 +825,8 @@ int buildJitKernel(simcu_ *r)
 {
 	JitConfig cfg;
 	cfg.threadsPerBlock = r->tpb; cfg.minBlocks = r->minBlocksUsed; cfg.gmin = r->ctl.gmin;
-	cfg.replay = r->replay; cfg.blockSync = r->blockSyncUsed; cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch; cfg.fmad = r->fmad;
+	cfg.replay = r->replay; cfg.blockSync = r->blockSyncUsed; cfg.syncGroup = r->syncGroup;
+	cfg.windows = !r->winTstep.empty(); cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch; cfg.fmad = r->fmad;
 	if (r->jit && r->jitProbes == r->probeRows && r->jitCfg == cfg && r->jitMeasures == r->measures)
 		return 0;
 	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows,
@@ -920,8 +956,18 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 				r->dReplayLin.upload(r->replayLin))
 			return -1;
 	}
+	if (!r->winTstep.empty()) {
+		if (r->interpreter) return fail("per-instance windows need the specialised kernel (interpreter = 0)");
+		std::vector<double> win((size_t)4 * M);
+		for (int i = 0; i < M; i++) {
+			win[i] = r->winTstep[i]; win[(size_t)M + i] = r->winTstop[i]; win[(size_t)2 * M + i] = r->winTmax[i];
+			win[(size_t)3 * M + i] = (r->minstepOpt < 0) ? r->winTstep[i] * 5e-5 : r->minstepOpt;
+		}
+		if (r->dWin.upload(win)) return -1;
+	}
 	for (int ph = 0; ph < 2; ph++) {
 		SimcuArgs &a = r->args[ph];
+		a.winst = r->winTstep.empty() ? nullptr : r->dWin.as<double>();
 		a.claimBelow = r->claimBelow;
 		a.replayOff = r->dReplayOff.as<int>(); a.replayTime = r->dReplayTime.as<double>();
 		a.replayFlag = r->dReplayFlag.as<int>();
@@ -1529,7 +1575,7 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	const std::vector<double> consts[2] = {p.constOP, p.constTran};
 	JitConfig cfg;
 	cfg.threadsPerBlock = tpb; cfg.minBlocks = r->minBlocks; cfg.gmin = r->ctl.gmin; cfg.replay = r->replay;
-	cfg.blockSync = (r->blockSync > 0); cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch;
+	cfg.blockSync = (r->blockSync > 0); cfg.syncGroup = r->syncGroup; cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch;
 	const std::string src = assembleSource(p, sched, active, consts, probeRows, r->measures, cfg);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;

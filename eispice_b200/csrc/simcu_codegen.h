@@ -19,13 +19,15 @@ struct JitConfig {
 	double gmin = 1e-15;      /* guard of every calculon division, folded into the code */
 	int replay = 0;           /* 1: replay an attempt log instead of own step control (tests) */
 	int blockSync = 0;        /* 1: the warps of a block start every attempt together */
+	int syncGroup = 0;        /* > 0: ... in groups of this many warps (named barriers) */
+	int windows = 0;          /* 1: per-instance analysis windows (tstep, tstop, tmax, minstep) */
 	double growthLimit = 1e6; /* LU multipliers above this are counted (pivot growth guard; <= 0: off) */
 	int tlinePrefetch = 0;    /* circuits with >= 2 T-lines: locate + prefetch pass before the step */
 	int fmad = 0;             /* 0: no a*b+c contraction: the reference's (and the oracle's) arithmetic */
 	bool operator==(const JitConfig &o) const
 	{
 		return threadsPerBlock == o.threadsPerBlock && minBlocks == o.minBlocks && gmin == o.gmin &&
-			replay == o.replay && blockSync == o.blockSync && growthLimit == o.growthLimit &&
+			replay == o.replay && blockSync == o.blockSync && syncGroup == o.syncGroup && windows == o.windows && growthLimit == o.growthLimit &&
 			tlinePrefetch == o.tlinePrefetch && fmad == o.fmad;
 	}
 };

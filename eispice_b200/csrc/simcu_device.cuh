@@ -41,6 +41,21 @@ DEVFN double simcuExp(double x) { return exp(x); }
 #endif
 #define Min3(x, y, z) ((x < y) ? ((z < x) ? z : x) : ((z < y) ? z : y))
 
+/* the analysis window: one for the whole batch (kernel constants), or - in a
+ * kernel specialised with SIMCU_WINDOWS - per instance (K-table generation:
+ * every (direction, speed) transient of a model has its own tstep / tstop) */
+#if defined(SIMCU_JIT) && defined(SIMCU_WINDOWS) && SIMCU_WINDOWS
+#define W_TSTEP(c) ((c).wTstep)
+#define W_TSTOP(c) ((c).wTstop)
+#define W_TMAX(c) ((c).wTmax)
+#define W_MINSTEP(c) ((c).wMinstep)
+#else
+#define W_TSTEP(c) ((c).a.ctl.tstep)
+#define W_TSTOP(c) ((c).a.ctl.tstop)
+#define W_TMAX(c) ((c).a.ctl.tmax)
+#define W_MINSTEP(c) ((c).a.ctl.minstep)
+#endif
+
 #ifdef SIMCU_JIT
 #define SIMCU_NH_LOOP SIMCU_NH
 #define SIMCU_N_LOOP SIMCU_N
@@ -82,6 +97,7 @@ struct Inst {
 	/* replay (test instrumentation): logged outcomes of the convergence tests of
 	 * this linearize pass, next bit to consume, own decisions that differed */
 	mutable int linMask, linBit, linDiff;
+	double wTstep, wTstop, wTmax, wMinstep;      /* SIMCU_WINDOWS: this instance's window */
 	mutable double Av[SIMCU_DIM(SIMCU_NNZ)], Bv[SIMCU_DIM(SIMCU_N)];
 	mutable double Xv[SIMCU_DIM(SIMCU_N)], Xa[SIMCU_DIM(SIMCU_N)];
 	mutable double sv[SIMCU_DIM(SIMCU_SD)];
@@ -419,7 +435,7 @@ DEV void itInitialize(const Inst &c, int sb, int ib, double ic, double ydtdx)
 		AGE(c, sb, RY, j) = 0.0; AGE(c, sb, RX, j) = ic; AGE(c, sb, RF, j) = ydtdx;
 	}
 	SIMCU_UNROLL
-	for (int j = 0; j < 3; j++) c.itH[j] = c.a.ctl.tstop;
+	for (int j = 0; j < 3; j++) c.itH[j] = W_TSTOP(c);
 }
 
 /* once per attempt, before the devices integrate: advance the shared time ring
@@ -517,7 +533,7 @@ DEV void itInitialize(const Inst &c, int sb, int ib, double ic, double ydtdx)
 {
 	c.D(sb) = 0.0; c.D(sb + 1) = 0.0; c.IS(ib) = 0;
 	for (int j = 0; j < 4; j++) {
-		RING(c, sb, RT, j) = 0.0; RING(c, sb, RH, j) = c.a.ctl.tstop;
+		RING(c, sb, RT, j) = 0.0; RING(c, sb, RH, j) = W_TSTOP(c);
 		RING(c, sb, RY, j) = 0.0; RING(c, sb, RX, j) = ic; RING(c, sb, RF, j) = ydtdx;
 	}
 }
@@ -596,7 +612,8 @@ DEV double wfValue(Inst &c, const int *d, int sb, int ib)
 {
 	const int wtype = d[DF_WTYPE], pa = d[DF_PARGS];
 	const SimcuControl &k = c.a.ctl;
-	const double tstep = k.tstep, tend = k.tstop + k.tstep, fmin = 1 / tend;
+	const double tstep = W_TSTEP(c), tend = W_TSTOP(c) + W_TSTEP(c), fmin = 1 / tend;
+	(void)k;
 	const double time = c.time;
 	switch (wtype) {
 	case 'p': {
@@ -640,7 +657,7 @@ DEV double wfValue(Inst &c, const int *d, int sb, int ib)
 			(v1 - v2) * (1 - exp(-(time - td2) / tau2));
 	}
 	case 'l': case 'c': {
-		const Table t = tableOf(c.a, d[DF_WTAB]);
+		const Table t = tableOf(c.a, d[DF_WTAB] + c.tableSet(d[DF_WSETSLOT]));
 		int idx = c.IS(ib + 1);
 		double v, dv;
 		pwCalcValue(t, idx, time, v, dv);
@@ -661,7 +678,8 @@ DEV void wfNextStep(Inst &c, const int *d, int ib, double &next)
 {
 	const int wtype = d[DF_WTYPE], pa = d[DF_PARGS];
 	const SimcuControl &k = c.a.ctl;
-	const double tstep = k.tstep, tend = k.tstop + k.tstep;
+	const double tstep = W_TSTEP(c), tend = W_TSTOP(c) + W_TSTEP(c);
+	(void)k;
 	const double time = c.time;
 	switch (wtype) {
 	case 'p': {
@@ -690,7 +708,7 @@ DEV void wfNextStep(Inst &c, const int *d, int ib, double &next)
 		break;
 	}
 	case 'l': case 'c': {
-		const Table t = tableOf(c.a, d[DF_WTAB]);
+		const Table t = tableOf(c.a, d[DF_WTAB] + c.tableSet(d[DF_WSETSLOT]));
 		int idx = c.IS(ib + 1);
 		const double tp = pwGetNextX(t, idx, time);
 		c.IS(ib + 1) = idx;
@@ -824,7 +842,7 @@ DEV void devLoad(Inst &c, const int *d, const int *bv = nullptr)
 		const int wtype = d[DF_WTYPE];
 		if (wtype == 0) dc = c.P(d[DF_PDC]);
 		else if (wtype == 'l' || wtype == 'c') {
-			const Table t = tableOf(c.a, d[DF_WTAB]);   /* waveform.c:385-389 */
+			const Table t = tableOf(c.a, d[DF_WTAB] + c.tableSet(d[DF_WSETSLOT]));   /* waveform.c:385-389 */
 			int idx = 0; double dv;
 			pwCalcValue(t, idx, 0.0, dc, dv);
 			c.IS(ib + 1) = idx;
@@ -1226,7 +1244,7 @@ DEV void devNextStep(Inst &c, const int *d, double &thisStep)
 	}
 	default: return;
 	}
-	if ((loc > c.a.ctl.minstep) && (loc < thisStep)) thisStep = loc;
+	if ((loc > W_MINSTEP(c)) && (loc < thisStep)) thisStep = loc;
 }
 
 #ifndef SIMCU_JIT
@@ -1403,7 +1421,7 @@ DEV void gridOutput(Inst &c, const int *rows, double tPrev, double tNow, bool fi
 	const SimcuArgs &a = c.a;
 	if (a.nprobes <= 0 || a.ngrid <= 0) return;
 	int g = c.gridIdx;
-	const double tstep = a.ctl.tstep, tstop = a.ctl.tstop;
+	const double tstep = W_TSTEP(c), tstop = W_TSTOP(c);
 	while (g < a.ngrid) {
 		double tg = g * tstep;
 		if (g == a.ngrid - 1 || tg > tstop) tg = tstop;

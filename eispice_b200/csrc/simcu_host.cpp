@@ -504,9 +504,22 @@ struct Flattener {
 			case DK_L: a = param(d, "L", d.val); if (rec) rec[DF_P0] = a; break;
 			case DK_V: case DK_I: {
 				a = param(d, "DC", d.val);
-				int first = -1, tab = -1;
+				int first = -1, tab = -1, wsetSlot = -1;
 				if (d.wtype == 'l' || d.wtype == 'c') {
 					if (!table(d.wtab, d.wtabLen, d.wtype, tab)) return false;
+					for (size_t s = 0; s < d.wsets.size(); s++) {
+						int id;
+						if (!table(d.wsets[s].first, d.wsets[s].second, d.wtype, id)) return false;
+					}
+					if (!d.instSet.empty()) {
+						for (size_t i = 0; i < d.instSet.size(); i++)
+							if (d.instSet[i] < 0 || d.instSet[i] > (int)d.wsets.size()) {
+								err = "table set index out of range for " + d.refdes;
+								return false;
+							}
+						wsetSlot = p.niinst++;
+						p.iinst.insert(p.iinst.end(), d.instSet.begin(), d.instSet.end());
+					}
 				} else if (d.wtype) {
 					for (int i = 0; i < 7; i++) {
 						char nm[3] = {'A', (char)('0' + i), 0};
@@ -514,7 +527,10 @@ struct Flattener {
 						if (i == 0) first = pid;
 					}
 				}
-				if (rec) { rec[DF_PDC] = a; rec[DF_WTYPE] = d.wtype; rec[DF_PARGS] = first; rec[DF_WTAB] = tab; }
+				if (rec) {
+					rec[DF_PDC] = a; rec[DF_WTYPE] = d.wtype; rec[DF_PARGS] = first; rec[DF_WTAB] = tab;
+					rec[DF_WSETSLOT] = wsetSlot;
+				}
 				break;
 			}
 			case DK_T:

@@ -48,6 +48,7 @@ struct Dev {
 	char wtype = 0;
 	const double *wargs[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	double **wtab = nullptr; int *wtabLen = nullptr;
+	std::vector<std::pair<double **, int *> > wsets;   /* further PWL / PWC tables (set 1, 2, ...) */
 	std::vector<TableSet> sets; char viType = 'l', taType = 'l';
 	CalcProg calc; bool usesTime = false;
 	std::vector<int> bvRow, bvCalcVar;

@@ -32,6 +32,12 @@
 #ifndef SIMCU_BLOCKSYNC
 #define SIMCU_BLOCKSYNC 0
 #endif
+#ifndef SIMCU_SYNCGROUP
+#define SIMCU_SYNCGROUP 0
+#endif
+#ifndef SIMCU_WINDOWS
+#define SIMCU_WINDOWS 0
+#endif
 
 /* statistics and status of a finished (or failed) instance; the data of an
  * instance with status != 0 is NaN from the failure time on */
@@ -100,7 +106,21 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 		 * loop body is several times the 32 KB L1.5 I-cache; unsynchronised, every
 		 * warp streams it from L2 on its own).  A warp's trip already waits for
 		 * its slowest lane, so waiting for the slowest warp costs little. */
+#if SIMCU_SYNCGROUP > 0
+		/* ... in groups of SIMCU_SYNCGROUP warps (named barrier + OR reduction) */
+		{
+			int any;
+			const int vote = (busy || !exhausted) ? 1 : 0;
+			const int grp = (threadIdx.x >> 5) / SIMCU_SYNCGROUP;
+			const int first = grp * SIMCU_SYNCGROUP * 32;
+			const int cnt = min((int)blockDim.x - first, SIMCU_SYNCGROUP * 32);
+			asm volatile("{ .reg .pred p, q; setp.ne.s32 q, %1, 0; bar.red.or.pred p, %2, %3, q; selp.s32 %0, 1, 0, p; }"
+					: "=r"(any) : "r"(vote), "r"(grp + 1), "r"(cnt) : "memory");
+			if (!any) break;
+		}
+#else
 		if (!__syncthreads_or((busy || !exhausted) ? 1 : 0)) break;
+#endif
 #endif
 		/* ---- claim: an idle lane takes the next instance of the queue once
 		 * few enough lanes of its warp are still busy (claimBelow = 31: at once;
@@ -116,6 +136,10 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 				const int inst = a.order ? __ldg(&a.order[q]) : q;
 				c.i = inst; c.hcount = 0; c.npts = 0; c.gridIdx = 0; c.time = 0.0; c.order = 1; c.err = 0;
 				c.growth = 0;
+#if SIMCU_WINDOWS
+				c.wTstep = a.winst[inst]; c.wTstop = a.winst[M + inst];
+				c.wTmax = a.winst[2 * M + inst]; c.wMinstep = a.winst[3 * M + inst];
+#endif
 				/* parameters of this instance: broadcast constants or its own column */
 				SIMCU_UNROLL
 				for (int p = 0; p < SIMCU_NPARAM; p++) {
@@ -173,7 +197,7 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 				nfact0 = nfact;
 #else
 				time = prevTime + thisStep;                 /* :157-161 */
-				if (time > k.tstop) { thisStep = k.tstop - prevTime; time = k.tstop; }
+				if (time > W_TSTOP(c)) { thisStep = W_TSTOP(c) - prevTime; time = W_TSTOP(c); }
 #endif
 				c.time = time; c.order = order;
 				brk = genStep(c);                           /* :167-173 */
@@ -224,11 +248,11 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 				genMeasures(c, meas, 0.0, 0.0, true);
 				SIMCU_UNROLL
 				for (int r = 0; r < SIMCU_N; r++) c.Xa[r] = c.Xv[r];
-				if (opOnly || !(0.0 < k.tstop)) { recordStep(c, hrows, 0.0); done = true; }
+				if (opOnly || !(0.0 < W_TSTOP(c))) { recordStep(c, hrows, 0.0); done = true; }
 				else {
 					genInitStep(c);
 					recordStep(c, hrows, 0.0);              /* :144 */
-					maxStep = ((k.tstep < k.tmax) ? k.tstep : k.tmax) / 100;   /* :109 */
+					maxStep = ((W_TSTEP(c) < W_TMAX(c)) ? W_TSTEP(c) : W_TMAX(c)) / 100;   /* :109 */
 					thisStep = maxStep;
 					genNextStep(c, thisStep);               /* :152-154 */
 					order = k.maxorder;                     /* :133 */
@@ -242,7 +266,7 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 			/* own decision: 0 accept, 1 LTE reject, 2 non-convergence */
 			int outcome = 2;
 			if (count < k.itl4) {
-				lteStep = k.tmax;                           /* :188-190 */
+				lteStep = W_TMAX(c);                         /* :188-190 */
 				genMinStep(c, lteStep);
 				outcome = (lteStep < (0.9 * thisStep)) ? 1 : 0;      /* :191 */
 			}
@@ -253,7 +277,7 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 #endif
 			if (c.err) done = true;
 			else if (outcome == 1) {                        /* :191-198 */
-				if (!SIMCU_REPLAY && lteStep < (k.tstep * 1e-9)) { c.err = SIMCU_ERR_TIMESTEP; done = true; }
+				if (!SIMCU_REPLAY && lteStep < (W_TSTEP(c) * 1e-9)) { c.err = SIMCU_ERR_TIMESTEP; done = true; }
 				else {
 					order = 1;
 					thisStep = lteStep;
@@ -266,18 +290,18 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 				for (int r = 0; r < SIMCU_N; r++) c.Xa[r] = c.Xv[r];
 				order = (order < k.maxorder) ? order + 1 : order;
 				prevTime = time;
-				if (brk) maxStep = Min3(lteStep, 0.1 * maxStep, k.tmax);
-				else maxStep = Min3(lteStep, 2 * maxStep, k.tmax);
+				if (brk) maxStep = Min3(lteStep, 0.1 * maxStep, W_TMAX(c));
+				else maxStep = Min3(lteStep, 2 * maxStep, W_TMAX(c));
 				accepted++;
 				recordStep(c, hrows, time);                 /* :144 of the next pass */
-				if (!(time < k.tstop)) done = true;
+				if (!(time < W_TSTOP(c))) done = true;
 				else {
 					thisStep = maxStep;                     /* :152-154 */
 					genNextStep(c, thisStep);
 				}
 			} else {                                        /* :201-214 */
 				thisStep = thisStep / 8;
-				if (!SIMCU_REPLAY && thisStep < (k.tstep * 1e-9)) { c.err = SIMCU_ERR_TIMESTEP; done = true; }
+				if (!SIMCU_REPLAY && thisStep < (W_TSTEP(c) * 1e-9)) { c.err = SIMCU_ERR_TIMESTEP; done = true; }
 				else {
 					order = (order > 1) ? order - 1 : order;
 					maxStep = maxStep / 8;

@@ -37,6 +37,7 @@ enum {
 #define DF_PARGS   11    /* first of 7 consecutive parameter ids */
 #define DF_WTAB    12    /* table id for 'l'/'c' */
 #define DF_SA0     13    /* V: A slots RK RJ KR JR */
+#define DF_WSETSLOT 17   /* per-instance int slot holding the waveform table set, -1: set 0 */
 /* T: parameter ids, 18 A slots, 6 history columns */
 #define DF_PZ0     9
 #define DF_PTD     10
@@ -162,6 +163,8 @@ typedef struct {
 	 * pass, entries [replayLinOff[i], replayLinOff[i+1]) of instance i */
 	const int *replayLinOff;
 	const int *replayLin;
+	/* per-instance analysis windows [tstep, tstop, tmax, minstep][M] (NULL: ctl's) */
+	const double *winst;
 } SimcuArgs;
 
 #endif

@@ -88,6 +88,8 @@ def lib():
     L.simcuAddVICurve.argtypes = [vp, cp, cp, cp, vp, vp, C.c_char, vp, vp, C.c_char]
     L.simcuSetInstanceParam.argtypes = [vp, cp, cp, vp, C.c_int]
     L.simcuAddVITableSet.argtypes = [vp, cp, vp, vp, vp, vp]
+    L.simcuAddSourceTableSet.argtypes = [vp, cp, vp, vp]
+    L.simcuSetInstanceWindow.argtypes = [vp, vp, vp, vp, C.c_int]
     L.simcuSetInstanceTableSet.argtypes = [vp, cp, vp, C.c_int]
     L.simcuSetOption.argtypes = [vp, cp, C.c_double]
     L.simcuSetPivots.argtypes = [vp, C.c_int, vp, vp, C.c_int]
@@ -225,6 +227,12 @@ class Engine:
                     self._keep.append(args)
                     rc = L.simcuAddSource(h, _b(ref), _b(d[2]), _b(d[3]), _b(d[4]),
                                           dc, _b(wave[0]), args)
+                    # further waveform tables (set 1, 2, ...): wave = (kind, table, [tables])
+                    for s, extra in enumerate(wave[2] if len(wave) > 2 else [], 1):
+                        if rc != 0:
+                            break
+                        tp, tl = self._tab(extra)
+                        rc = 0 if L.simcuAddSourceTableSet(h, _b(ref), tp, tl) == s else -1
             elif k == "B":
                 eq = C.create_string_buffer(_b(d[5]))
                 self._keep.append(eq)
@@ -279,6 +287,8 @@ class Engine:
     def c_name(self, refdes, attr):
         """Member name of the Python device -> parameter name of the C-ABI."""
         d = self._kinds[refdes]
+        if d[0] in ("V", "I") and len(attr) == 2 and attr[0] == "A" and attr[1] in "0123456":
+            return attr               # the C-ABI's own name of a waveform argument slot
         if d[0] in ("V", "I") and attr != "DC":
             wave = d[6]
             if wave is None or wave[0] not in _WAVE_NAMES:
@@ -304,6 +314,17 @@ class Engine:
             if rc != 0:
                 raise KeyError(key)
             self._params[key] = a
+
+    def set_windows(self, tstep=None, tstop=None, tmax=None):
+        """Per-instance analysis windows (arrays [M]); None returns to one window."""
+        if tstep is None:
+            self.L.simcuSetInstanceWindow(self.h, None, None, None, 1)
+            return
+        M = self.num_instances
+        a = [np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (M,)))
+             for x in (tstep, tstop, tmax if tmax is not None else 0.0)]
+        if self.L.simcuSetInstanceWindow(self.h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, 1):
+            raise ValueError("bad analysis windows")
 
     def set_pivots(self, phase, pc, pr):
         pc = np.ascontiguousarray(pc, dtype=np.int32)

@@ -132,3 +132,173 @@ def driver_k_tables(model, runner=None):
             up[direction][speed] = ku
             down[direction][speed] = kd
     return {"pullup_k": up, "pulldown_k": down}
+
+
+# ---------------------------------------------------------------------------
+# Batched generation: every (model, direction, speed) transient is one INSTANCE
+# of a batch per extraction-circuit topology (reference: 6 separate transients
+# per driver model at parse time, module/ibis_parser.py:500-510).
+# ---------------------------------------------------------------------------
+def _signature(netlist):
+    """What must be equal for two extraction circuits to share a batch: device
+    kinds, names, nodes, B equations, waveform kinds and which VI devices carry a
+    TA table - everything except values and table contents."""
+    sig = []
+    for d in netlist:
+        k = d[0]
+        if k in ("R", "C", "L"):
+            sig.append((k, d[1], d[2], d[3]))
+        elif k in ("V", "I"):
+            sig.append((k, d[1], d[2], d[3], None if d[6] is None else d[6][0]))
+        elif k == "B":
+            sig.append((k, d[1], d[2], d[3], d[4], d[5]))
+        elif k == "VI":
+            sig.append((k, d[1], d[2], d[3], tuple(t[0] for t in d[4]), d[5] is not None))
+        else:
+            sig.append(tuple(d[:6]))
+    return tuple(sig)
+
+
+def _table_key(t):
+    return np.ascontiguousarray(np.asarray(t, dtype=np.float64)).tobytes()
+
+
+def merge_netlists(netlists):
+    """Several netlists of one signature -> (netlist with table sets, params):
+    scalars that differ become per-instance arrays "Refdes.member", tables that
+    differ become table sets selected by "Refdes.set"."""
+    base = netlists[0]
+    n = len(netlists)
+    merged, params = [], {}
+    for k, d0 in enumerate(base):
+        devs = [nl[k] for nl in netlists]
+        kind, ref = d0[0], d0[1]
+        if kind in ("R", "C", "L"):
+            vals = np.array([float(d[4]) for d in devs])
+            if (vals != vals[0]).any():
+                params["%s.%s" % (ref, kind)] = vals
+            merged.append(d0)
+        elif kind in ("V", "I"):
+            dc = np.array([float(d[5]) for d in devs])
+            if (dc != dc[0]).any():
+                params["%s.DC" % ref] = dc
+            wave = d0[6]
+            if wave is None:
+                merged.append(d0)
+            elif wave[0] in ("l", "c"):
+                keys, tables, sel = {}, [], []
+                for d in devs:
+                    key = _table_key(d[6][1])
+                    if key not in keys:
+                        keys[key] = len(tables)
+                        tables.append(d[6][1])
+                    sel.append(keys[key])
+                if len(tables) > 1:
+                    params["%s.set" % ref] = np.array(sel, dtype=np.int32)
+                merged.append(tuple(d0[:6]) + ((wave[0], tables[0], tables[1:]),))
+            else:
+                args = np.array([[float(x) for x in d[6][1]] for d in devs])
+                for j in range(args.shape[1]):
+                    col = args[:, j]
+                    same = (col == col[0]) | (np.isinf(col) & np.isinf(col[0]))
+                    if not same.all():
+                        params["%s.A%d" % (ref, j)] = col
+                merged.append(d0)
+        elif kind == "VI":
+            vi_keys, vis, tas, sel = {}, [], [], []
+            for d in devs:
+                key = _table_key(d[4][0][1]) + (b"" if d[5] is None else _table_key(d[5][0][1]))
+                if key not in vi_keys:
+                    vi_keys[key] = len(vis)
+                    vis.append(d[4][0])
+                    if d[5] is not None:
+                        tas.append(d[5][0])
+                sel.append(vi_keys[key])
+            if len(vis) > 1:
+                params["%s.set" % ref] = np.array(sel, dtype=np.int32)
+            merged.append((kind, ref, d0[2], d0[3], vis, tas if d0[5] is not None else None))
+        else:
+            merged.append(d0)
+    for key in params:
+        assert len(params[key]) == n
+    return merged, params
+
+
+def instance_netlist(merged, params, j):
+    """Instance j of a merged netlist as a plain netlist (checks merge_netlists;
+    also what the CPU oracle would run for that instance)."""
+    out = []
+    for d in merged:
+        d = list(d)
+        kind, ref = d[0], d[1]
+        if kind in ("R", "C", "L") and "%s.%s" % (ref, kind) in params:
+            d[4] = float(params["%s.%s" % (ref, kind)][j])
+        elif kind in ("V", "I"):
+            if "%s.DC" % ref in params:
+                d[5] = float(params["%s.DC" % ref][j])
+            wave = d[6]
+            if wave is not None and wave[0] in ("l", "c"):
+                tables = [wave[1]] + list(wave[2] if len(wave) > 2 else [])
+                s = int(params["%s.set" % ref][j]) if "%s.set" % ref in params else 0
+                d[6] = (wave[0], tables[s])
+            elif wave is not None:
+                args = list(wave[1])
+                for a in range(len(args)):
+                    if "%s.A%d" % (ref, a) in params:
+                        args[a] = float(params["%s.A%d" % (ref, a)][j])
+                d[6] = (wave[0], args)
+        elif kind == "VI":
+            s = int(params["%s.set" % ref][j]) if "%s.set" % ref in params else 0
+            d[4] = [d[4][s]]
+            d[5] = None if d[5] is None else [d[5][s]]
+        out.append(tuple(d))
+    return out
+
+
+def driver_k_tables_batched(models, tstep_divisor=10, max_points=60000):
+    """pullup_k / pulldown_k of every driver model in ``models`` ({name: model}):
+    all their (direction, speed) transients run as instances of ONE batch per
+    extraction-circuit topology on the CUDA engine, each with its own analysis
+    window (simcuSetInstanceWindow), its own V-t waveform / V-I tables (table
+    sets) and its own scalars.  Returns ({name: {"pullup_k":…, "pulldown_k":…}},
+    info) with info = number of batches, instances and accepted steps."""
+    from . import engine
+    jobs = []
+    for name, model in models.items():
+        for direction in (Rising, Falling):
+            for speed in (Typical, Minimum, Maximum):
+                cct, tstep, tstop = k_circuit(model, direction, speed, tstep_divisor)
+                jobs.append((name, direction, speed, cct.netlist(), tstep, tstop))
+    groups = {}
+    for job in jobs:
+        groups.setdefault(_signature(job[3]), []).append(job)
+    out = {name: {"pullup_k": {Rising: {}, Falling: {}}, "pulldown_k": {Rising: {}, Falling: {}}}
+           for name in models}
+    info = {"batches": 0, "instances": 0, "accepted": 0, "failed": 0}
+    for group in groups.values():
+        merged, params = merge_netlists([g[3] for g in group])
+        n = len(group)
+        eng = engine.Engine(merged, n)
+        try:
+            if params:
+                eng.set_params(params)
+            tsteps = np.array([g[4] for g in group])
+            tstops = np.array([g[5] for g in group])
+            eng.set_windows(tsteps, tstops)
+            res = eng.tran_batch(float(np.median(tsteps)), float(tstops.max()), 0.0, None, [],
+                                 raw_max_points=max_points, raw_count=n)
+            raws = eng.fetch_raw_all(max_points)
+            names = eng.variables()
+        finally:
+            eng.close()
+        t, iu, idn = names.index("time"), names.index("v(ku)"), names.index("v(kd)")
+        for j, (name, direction, speed, _, _, _) in enumerate(group):
+            if res.status[j] != 0:
+                info["failed"] += 1
+                continue
+            out[name]["pullup_k"][direction][speed] = raws[j][:, [t, iu]][1:]
+            out[name]["pulldown_k"][direction][speed] = raws[j][:, [t, idn]][1:]
+        info["batches"] += 1
+        info["instances"] += n
+        info["accepted"] += int(res.stats["accepted"])
+    return out, info

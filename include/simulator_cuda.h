@@ -128,8 +128,20 @@ int simcuSetInstanceParam(simcu_ *r, char *refdes, char *name,
  * the set index (>= 1) or -1.  Tables are borrowed like simcuAddVICurve's. */
 int simcuAddVITableSet(simcu_ *r, char *refdes, double **vi, int *viLength,
 		double **ta, int *taLength);
-/* Which table set each instance uses (default 0). Copied immediately. */
+/* Further waveform tables for an existing PWL / PWC source (stimulus 'l' / 'c'
+ * of simcuAddSource); returns the set index (>= 1) or -1.  Borrowed likewise. */
+int simcuAddSourceTableSet(simcu_ *r, char *refdes, double **table, int *length);
+/* Which table set each instance uses (default 0), for a VI device or a PWL /
+ * PWC source. Copied immediately. */
 int simcuSetInstanceTableSet(simcu_ *r, char *refdes, const int *setIndex,
+		int stride);
+/* Per-instance analysis windows: instance i runs tran(tstep[i*stride],
+ * tstop[i*stride], tmax[i*stride]) (tmax = NULL or 0: the reference's default,
+ * core/simulator.c:91-94); the tstep / tstop of the run call then only define
+ * the output grid.  For batches of DIFFERENT analyses of one topology - the six
+ * (direction, speed) transients of an IBIS model's K tables
+ * (module/ibis_parser.py:500-510).  tstep = NULL returns to one window. */
+int simcuSetInstanceWindow(simcu_ *r, const double *tstep, const double *tstop, const double *tmax,
 		int stride);
 /* Options: reltol vntol abstol captol chgtol trtol gmin itl1 itl4 maxorder
  * minstep (control.h:34-56); hist_records, max_attempts, attempts_per_launch,

@@ -101,3 +101,72 @@ def test_link_with_gpu_generated_k_tables():
     vb = np.interp(grid, b.t, b.results[:, b.variables.index("v(vo)")])
     assert np.abs(va - vb).max() < parity.RELTOL * np.abs(vb).max() + parity.VNTOL
     assert a.check_v('vo', 2.942970279e-01, '4.7n') or abs(a.v['vo']('4.7n') - 2.942970279e-01) < 1e-3
+
+
+def test_merged_k_circuits_expand_to_the_single_circuits():
+    """Batched K-table generation (CPU side): the extraction circuits of all
+    (model, direction, speed) combinations group into a few topologies; merging a
+    group into one netlist with table sets + per-instance arrays and expanding
+    instance j again gives exactly job j's own netlist."""
+    models, _ = circuits.ibis_fixture()
+    jobs = []
+    for name in DRIVERS:
+        for direction, speed in COMBOS:
+            cct, tstep, tstop = ibis_driver.k_circuit(models[name], direction, speed)
+            jobs.append((name, direction, speed, cct.netlist(), tstep, tstop))
+    groups = {}
+    for job in jobs:
+        groups.setdefault(ibis_driver._signature(job[3]), []).append(job)
+    assert 1 <= len(groups) <= 4 and sum(len(g) for g in groups.values()) == 18
+    for group in groups.values():
+        merged, params = ibis_driver.merge_netlists([g[3] for g in group])
+        for j, job in enumerate(group):
+            mine = ibis_driver.instance_netlist(merged, params, j)
+            assert len(mine) == len(job[3])
+            for a, b in zip(mine, job[3]):
+                assert a[:4] == b[:4]
+                if a[0] in ("R", "C", "L"):
+                    assert float(a[4]) == float(b[4])
+                elif a[0] in ("V", "I"):
+                    assert float(a[5]) == float(b[5])
+                    if b[6] is not None and b[6][0] in ("l", "c"):
+                        assert np.array_equal(np.asarray(a[6][1], float), np.asarray(b[6][1], float))
+                    elif b[6] is not None:
+                        x, y = np.array(a[6][1], float), np.array(b[6][1], float)
+                        assert ((x == y) | (np.isinf(x) & np.isinf(y))).all()
+                elif a[0] == "VI":
+                    assert np.array_equal(np.asarray(a[4][0][1], float), np.asarray(b[4][0][1], float))
+                    assert (a[5] is None) == (b[5] is None)
+        # instance j of the merged netlist simulates like job j (oracle, one instance)
+        j = len(group) - 1
+        do, vo = backends.OracleSim(ibis_driver.instance_netlist(merged, params, j)).tran(group[j][4], group[j][5])
+        dj, vj = backends.OracleSim(group[j][3]).tran(group[j][4], group[j][5])
+        assert vo == vj and np.array_equal(do, dj)
+
+
+@pytest.mark.gpu
+def test_k_tables_batched_on_the_gpu():
+    """All 18 K-table transients of the fixture's three driver models as instances
+    of one batch per extraction topology (per-instance analysis windows, waveform
+    and V-I table sets): every table equals the reference's as a function of
+    time at the reference's reltol."""
+    import time
+    models, _ = circuits.ibis_fixture()
+    drivers = {name: models[name] for name in DRIVERS}
+    t0 = time.time()
+    tables, info = ibis_driver.driver_k_tables_batched(drivers)
+    cold = time.time() - t0
+    t0 = time.time()
+    tables, info = ibis_driver.driver_k_tables_batched(drivers)
+    warm = time.time() - t0
+    assert info["instances"] == 18 and info["failed"] == 0 and info["batches"] <= 4
+    for name in DRIVERS:
+        for direction, speed in COMBOS:
+            for kind in ("pullup_k", "pulldown_k"):
+                mine, gold = tables[name][kind][direction][speed], models[name][kind][direction][speed]
+                grid = np.linspace(gold[0, 0], gold[-1, 0], 2000)
+                a = np.interp(grid, mine[:, 0], mine[:, 1])
+                b = np.interp(grid, gold[:, 0], gold[:, 1])
+                assert np.abs(a - b).max() <= parity.RELTOL * max(1.0, np.abs(b).max()), (name, direction, speed, kind)
+    print("K tables of %d transients in %d batches: %.2f s cold (NVRTC), %.3f s warm; reference: 0.22 s on one core"
+          % (info["instances"], info["batches"], cold, warm))
