@@ -1575,12 +1575,13 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	const std::vector<double> consts[2] = {p.constOP, p.constTran};
 	JitConfig cfg;
 	cfg.threadsPerBlock = tpb; cfg.minBlocks = r->minBlocks; cfg.gmin = r->ctl.gmin; cfg.replay = r->replay;
-	cfg.blockSync = (r->blockSync > 0); cfg.syncGroup = r->syncGroup; cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch;
+	cfg.blockSync = (r->blockSync > 0); cfg.syncGroup = r->syncGroup; cfg.growthLimit = r->growthLimit;
+	cfg.windows = !r->winTstep.empty(); cfg.fmad = r->fmad; cfg.tlinePrefetch = r->tlinePrefetch;
 	const std::string src = assembleSource(p, sched, active, consts, probeRows, r->measures, cfg);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;
 	std::string err;
-	if (!jitCompile(src, k, err)) return fail("%s", err.c_str());
+	if (!jitCompile(src, k, err, cfg.fmad != 0)) return fail("%s", err.c_str());
 	if (cubinBytes) *cubinBytes = (int)k.cubin.size();
 	return 0;
 }

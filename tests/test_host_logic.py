@@ -503,3 +503,35 @@ def test_measure_and_probe_names_are_checked_on_the_host():
         eng.close()
     finally:
         L.simcuSetOption(None, b"quiet", 0.0)
+
+
+def test_windows_and_source_table_sets_compile_without_a_gpu():
+    """Per-instance analysis windows and PWL-source table sets (batched K-table
+    generation): the specialised kernel is generated with SIMCU_WINDOWS and
+    compiles for sm_100a; bad input is rejected at the C-ABI."""
+    import eispice_b200 as eispice
+    cct = circuits._new("pwl sets")
+    t0 = [[0, 0], [1e-9, 1], [2e-9, 0]]
+    t1 = [[0, 0], [2e-9, 2], [4e-9, 0]]
+    cct.V1 = eispice.V('in', 0, 0, eispice.PWL(t0))
+    cct.R1 = eispice.R('in', 'out', 50)
+    cct.C1 = eispice.C('out', 0, '1p')
+    nl = [tuple(d[:6]) + ((d[6][0], d[6][1], [t1]),) if d[1] == "V1" else d for d in cct.netlist()]
+    eng = engine.Engine(nl, 3)
+    eng.set_params({"V1.set": np.array([0, 1, 1], dtype=np.int32)})
+    eng.set_params({"V1.set": np.array([0, 2, 1], dtype=np.int32)})          # only sets 0 and 1 exist
+    engine.lib().simcuSetOption(None, b"quiet", 1.0)
+    with pytest.raises(RuntimeError):
+        eng.compile_only(["v(out)"])
+    engine.lib().simcuSetOption(None, b"quiet", 0.0)
+    eng.set_params({"V1.set": np.array([0, 1, 1], dtype=np.int32)})
+    eng.set_windows([1e-11, 2e-11, 2e-11], [2e-9, 4e-9, 4e-9])
+    src, nbytes = eng.compile_only(["v(out)"])
+    assert "#define SIMCU_WINDOWS 1" in src and nbytes > 10000
+    assert "DF_WSETSLOT" in src
+    with pytest.raises(ValueError):
+        eng.set_windows([1e-11, -1.0, 1e-11], [2e-9, 4e-9, 4e-9])
+    eng.set_windows(None)
+    src, _ = eng.compile_only(["v(out)"])
+    assert "#define SIMCU_WINDOWS 0" in src
+    eng.close()
