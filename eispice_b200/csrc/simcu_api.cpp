@@ -134,6 +134,11 @@ struct _simcu {
 	SimcuArgs args[2];
 	simcuStats_ stats;
 	/* device memory */
+	DBuf dTabDesc, dTabStage;
+	int stagePoints = 0;            /* table points staged in shared memory by every block */
+	bool stageOK = false;           /* this launch shape stages tables (one big block per SM) */
+	int smemTablesKB = -1;          /* budget for that (option smem_tables_kb; 0 = tables stay global, -1 = automatic) */
+	int smemTablesUsed = 0;
 	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
 		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
 		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2, dMeasure, dMeasureLevel,
@@ -157,7 +162,7 @@ struct _simcu {
 	{
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
 			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder, &dOrder2, &dMeasure,
-			&dMeasureLevel, &dReplayOff, &dReplayTime, &dReplayFlag, &dReplayLinOff, &dReplayLin, &dWin, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
+			&dMeasureLevel, &dReplayOff, &dReplayTime, &dReplayFlag, &dReplayLinOff, &dReplayLin, &dWin, &dTabDesc, &dTabStage, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
 			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dStatusT, &dOutRaw,
 			&dWs, &dRemaining};
 		for (size_t i = 0; i < sizeof all / sizeof all[0]; i++) all[i]->release();
@@ -557,6 +562,7 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "replay") r->replay = (value != 0.0);
 	else if (n == "block_sync") r->blockSync = (value < 0.0) ? -1 : (value != 0.0);
 	else if (n == "sync_group") r->syncGroup = std::max(0, std::min(15, (int)value));
+	else if (n == "smem_tables_kb") r->smemTablesKB = std::max(-1, std::min(200, (int)value));
 	else if (n == "growth_limit") r->growthLimit = value;
 	else if (n == "tline_prefetch") r->tlinePrefetch = (value != 0.0);
 	else if (n == "fmad") r->fmad = (value != 0.0);
@@ -647,6 +653,29 @@ int uploadParameters(simcu_ *r, cudaStream_t st)
 			r->dTabOff.upload(p.tabOff, st) || r->dTabType.upload(p.tabType, st) ||
 			r->dTabP.upload(p.tabP, st))
 		return -1;
+	/* table descriptors, and the tables every block stages in shared memory: V-I
+	 * tables first (looked up at every Newton iteration), then TA, then source
+	 * tables, in table order, as long as they fit the budget */
+	{
+		const int ntab = (int)p.tabType.size();
+		std::vector<int> desc((size_t)4 * std::max(1, ntab), -1);
+		std::vector<double> stage;
+		const size_t budget = r->stageOK ? (size_t)r->smemTablesUsed * 1024 / 32 : 0;
+		for (int t = 0; t < ntab; t++) {
+			desc[4 * t] = p.tabOff[t]; desc[4 * t + 1] = p.tabOff[t + 1] - p.tabOff[t];
+			desc[4 * t + 2] = p.tabType[t]; desc[4 * t + 3] = -1;
+		}
+		for (int klass = 0; klass < 3; klass++)
+			for (int t = 0; t < ntab; t++) {
+				const size_t len = (size_t)desc[4 * t + 1];
+				if (p.tabClass[t] != klass || stage.size() / 4 + len > budget) continue;
+				desc[4 * t + 3] = (int)(stage.size() / 4);
+				stage.insert(stage.end(), p.tabP.begin() + 4 * (size_t)p.tabOff[t],
+						p.tabP.begin() + 4 * (size_t)p.tabOff[t + 1]);
+			}
+		r->stagePoints = (int)(stage.size() / 4);
+		if (r->dTabDesc.upload(desc, st) || r->dTabStage.upload(stage, st)) return -1;
+	}
 	/* processing order: stable sort by the tuple of table-set indices */
 	const int *order = nullptr;
 	if (p.niinst > 0 && !r->keepOrder && r->orderKey == p.iinst && r->dOrder.p) {
@@ -673,6 +702,8 @@ int uploadParameters(simcu_ *r, cudaStream_t st)
 		a.pinst = r->dPinst.as<double>(); a.iinst = r->dIinst.as<int>();
 		a.tabOff = r->dTabOff.as<int>(); a.tabType = r->dTabType.as<int>();
 		a.tabP = r->dTabP.as<double>();
+		a.tabDesc = r->dTabDesc.as<int>(); a.tabStage = r->dTabStage.as<double>();
+		a.stagePoints = r->stagePoints;
 	}
 	return 0;
 }
@@ -827,6 +858,7 @@ int buildJitKernel(simcu_ *r)
 	cfg.threadsPerBlock = r->tpb; cfg.minBlocks = r->minBlocksUsed; cfg.gmin = r->ctl.gmin;
 	cfg.replay = r->replay; cfg.blockSync = r->blockSyncUsed; cfg.syncGroup = r->syncGroup;
 	cfg.windows = !r->winTstep.empty(); cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch; cfg.fmad = r->fmad;
+	cfg.smemTab = (r->stagePoints > 0);
 	if (r->jit && r->jitProbes == r->probeRows && r->jitCfg == cfg && r->jitMeasures == r->measures)
 		return 0;
 	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows,
@@ -945,6 +977,22 @@ int prepare(simcu_ *r, double tstep, double tstop, double tmax, char *probes[], 
 		a.remaining = r->dRemaining.as<int>();
 		a.counter = r->dRemaining.as<int>() + 1;
 		a.stopBeforeSolve = 0;
+	}
+	{
+		/* tables are staged in shared memory only by the one-big-block-per-SM shapes
+		 * (several small blocks per SM would each need their own copy) */
+		int smsEarly = 148, devEarly = 0;
+		if (cudaGetDevice(&devEarly) == cudaSuccess)
+			cudaDeviceGetAttribute(&smsEarly, cudaDevAttrMultiProcessorCount, devEarly);
+		const bool fullEarly = (long long)M >= (long long)smsEarly * 256;
+		const int wsEarly = p.stateDoubles + p.nnzA + 3 * p.N + (int)p.pmap.size();
+		/* automatic: 100 kB (all V-I tables of the IBIS links) for the 256-thread /
+		 * 255-register shape, where L1 can spare it (cfg4 +1 %); none for the
+		 * 896-thread shape, whose spilled state needs all of L1 (cfg5 -5 %) */
+		r->smemTablesUsed = (r->smemTablesKB >= 0) ? r->smemTablesKB
+			: ((r->tpbOpt == 0 && fullEarly && p.N > 12 && wsEarly < 600) ? 100 : 0);
+		r->stageOK = !r->interpreter && r->smemTablesUsed > 0 &&
+			((r->tpbOpt == 0 && fullEarly && p.N > 12) || r->tpbOpt >= 256);
 	}
 	if (uploadParameters(r, 0)) return -1;
 	if (uploadSchedule(r, 0) || uploadSchedule(r, 1)) return -1;
@@ -1113,8 +1161,14 @@ int runDevice(simcu_ *r, cudaStream_t st, bool opOnly)
 			a1.order = r->dOrder2.as<int>(); a1.count = 1; blocks = 1;
 		}
 		void *params[] = {(void *)&a1, (void *)&op};
+		const size_t smem = (size_t)r->stagePoints * 32;          /* staged tables */
+		if (smem > 0) {
+			CU(cudaFuncSetAttribute((const void *)r->jit->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			CU(cudaFuncSetAttribute((const void *)r->jit->kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+					(int)std::min<size_t>(100, (smem * 100 + 228 * 1024 - 1) / (228 * 1024))));
+		}
 		cudaError_t e = cudaLaunchKernel((const void *)r->jit->kernel, dim3(blocks), dim3(r->tpb),
-				params, 0, st);
+				params, smem, st);
 		if (e != cudaSuccess) return fail("specialised kernel launch failed: %s", cudaGetErrorString(e));
 		launches = 1;
 		r->stats.historyRetries = 0;
@@ -1154,7 +1208,7 @@ int runDevice(simcu_ *r, cudaStream_t st, bool opOnly)
 				a2.order = r->dOrder2.as<int>();
 				CU(cudaMemsetAsync(r->dRemaining.p, 0, 2 * sizeof(int), st));
 				void *params2[] = {(void *)&a2, (void *)&op};
-				e = cudaLaunchKernel((const void *)r->jit->kernel, dim3(blocks2), dim3(r->tpb), params2, 0, st);
+				e = cudaLaunchKernel((const void *)r->jit->kernel, dim3(blocks2), dim3(r->tpb), params2, smem, st);
 				if (e != cudaSuccess) return fail("retry launch failed: %s", cudaGetErrorString(e));
 				launches++;
 				r->stats.historyRetries = n2;
@@ -1576,7 +1630,7 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	JitConfig cfg;
 	cfg.threadsPerBlock = tpb; cfg.minBlocks = r->minBlocks; cfg.gmin = r->ctl.gmin; cfg.replay = r->replay;
 	cfg.blockSync = (r->blockSync > 0); cfg.syncGroup = r->syncGroup; cfg.growthLimit = r->growthLimit;
-	cfg.windows = !r->winTstep.empty(); cfg.fmad = r->fmad; cfg.tlinePrefetch = r->tlinePrefetch;
+	cfg.windows = !r->winTstep.empty(); cfg.fmad = r->fmad; cfg.smemTab = (r->smemTablesKB > 0); cfg.tlinePrefetch = r->tlinePrefetch;
 	const std::string src = assembleSource(p, sched, active, consts, probeRows, r->measures, cfg);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;

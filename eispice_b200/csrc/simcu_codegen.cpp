@@ -587,7 +587,7 @@ std::string generatePrelude(const Program &p, int numProbes, int numMeasures, co
 	o.f("#define SIMCU_NMEASURES %d\n", numMeasures);
 	o.f("#define SIMCU_REPLAY %d\n", cfg.replay ? 1 : 0);
 	o.f("#define SIMCU_BLOCKSYNC %d\n#define SIMCU_SYNCGROUP %d\n", cfg.blockSync ? 1 : 0, cfg.syncGroup);
-	o.f("#define SIMCU_WINDOWS %d\n", cfg.windows ? 1 : 0);
+	o.f("#define SIMCU_WINDOWS %d\n#define SIMCU_SMEMTAB %d\n", cfg.windows ? 1 : 0, cfg.smemTab ? 1 : 0);
 	o.f("#define SIMCU_FMAD %d   /* compiled with --fmad=%s */\n", cfg.fmad ? 1 : 0, cfg.fmad ? "true" : "false");
 	o.f("#define HUGE_VAL (__longlong_as_double(0x7ff0000000000000LL))\n");
 	o.f("#define SIMCU_GMIN (%s)\n", lit(gmin).c_str());

@@ -21,13 +21,14 @@ struct JitConfig {
 	int blockSync = 0;        /* 1: the warps of a block start every attempt together */
 	int syncGroup = 0;        /* > 0: ... in groups of this many warps (named barriers) */
 	int windows = 0;          /* 1: per-instance analysis windows (tstep, tstop, tmax, minstep) */
+	int smemTab = 0;          /* 1: hot tables staged in shared memory */
 	double growthLimit = 1e6; /* LU multipliers above this are counted (pivot growth guard; <= 0: off) */
 	int tlinePrefetch = 0;    /* circuits with >= 2 T-lines: locate + prefetch pass before the step */
 	int fmad = 0;             /* 0: no a*b+c contraction: the reference's (and the oracle's) arithmetic */
 	bool operator==(const JitConfig &o) const
 	{
 		return threadsPerBlock == o.threadsPerBlock && minBlocks == o.minBlocks && gmin == o.gmin &&
-			replay == o.replay && blockSync == o.blockSync && syncGroup == o.syncGroup && windows == o.windows && growthLimit == o.growthLimit &&
+			replay == o.replay && blockSync == o.blockSync && syncGroup == o.syncGroup && windows == o.windows && smemTab == o.smemTab && growthLimit == o.growthLimit &&
 			tlinePrefetch == o.tlinePrefetch && fmad == o.fmad;
 	}
 };

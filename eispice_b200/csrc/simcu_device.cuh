@@ -180,10 +180,20 @@ DEV const int *bvOf(const Inst &c, const int *d, const int *) { return c.a.bvar 
 struct Table { const double *p; int len; int type; };
 struct TabEntry { double x, y, m, xn; };
 
+#if defined(SIMCU_JIT) && defined(SIMCU_SMEMTAB) && SIMCU_SMEMTAB
+/* the tables this topology looks up most (V-I tables first) are staged in
+ * shared memory by every block (simcu_jit_kernel.cuh); Table.p then points into
+ * the shared window, so entries are read with plain (generic) loads */
+extern __shared__ double simcuSmemTab[];
+#define TAB_LD(p) (*(p))
+#else
+#define TAB_LD(p) __ldg(p)
+#endif
+
 DEV TabEntry tabLoad(const Table &t, int i)
 {
-	const double2 a = __ldg(reinterpret_cast<const double2 *>(t.p + 4 * (size_t)i));
-	const double2 b = __ldg(reinterpret_cast<const double2 *>(t.p + 4 * (size_t)i) + 1);
+	const double2 a = TAB_LD(reinterpret_cast<const double2 *>(t.p + 4 * (size_t)i));
+	const double2 b = TAB_LD(reinterpret_cast<const double2 *>(t.p + 4 * (size_t)i) + 1);
 	TabEntry e;
 	e.x = a.x; e.y = a.y; e.m = b.x; e.xn = b.y;
 	return e;
@@ -192,10 +202,14 @@ DEV TabEntry tabLoad(const Table &t, int i)
 DEV Table tableOf(const SimcuArgs &a, int t)
 {
 	Table r;
-	const int off = __ldg(&a.tabOff[t]);
-	r.len = __ldg(&a.tabOff[t + 1]) - off;
-	r.type = __ldg(&a.tabType[t]);
-	r.p = a.tabP + 4 * (size_t)off;
+	const int4 d = __ldg(reinterpret_cast<const int4 *>(a.tabDesc) + t);     /* one 16-byte fetch */
+	r.len = d.y;
+	r.type = d.z;
+#if defined(SIMCU_JIT) && defined(SIMCU_SMEMTAB) && SIMCU_SMEMTAB
+	r.p = (d.w >= 0) ? simcuSmemTab + 4 * (size_t)d.w : a.tabP + 4 * (size_t)d.x;
+#else
+	r.p = a.tabP + 4 * (size_t)d.x;
+#endif
 	return r;
 }
 

@@ -447,7 +447,7 @@ struct Flattener {
 	}
 
 	/* piecewise.c:183-201 (linear slopes) and :108-181 (natural cubic spline) */
-	bool table(double **src, const int *len, char type, int &id)
+	bool table(double **src, const int *len, char type, int &id, int klass = 2)
 	{
 		if (!src || !*src || !len || *len < 1) { err = "missing table"; return false; }
 		const int n = *len;
@@ -479,6 +479,7 @@ struct Flattener {
 			for (int i = last - 1; i > 0; i--) m[i] = (v[i] - h[i] * m[i + 1]) / u[i];
 		}
 		p.tabType.push_back(type);
+		p.tabClass.push_back(klass);
 		for (int i = 0; i < n; i++) {
 			p.tabP.push_back(x[i]); p.tabP.push_back(y[i]); p.tabP.push_back(m[i]);
 			p.tabP.push_back((i + 1 < n) ? x[i + 1] : HUGE_VAL);
@@ -492,7 +493,7 @@ struct Flattener {
 	{
 		p.pmap.clear(); p.pconst.clear(); p.pinst.clear(); p.iinst.clear();
 		p.ninst = 0; p.niinst = 0;
-		p.tabOff.assign(1, 0); p.tabType.clear();
+		p.tabOff.assign(1, 0); p.tabType.clear(); p.tabClass.clear();
 		p.tabP.clear();
 		for (size_t k = 0; k < nl.devs.size(); k++) {
 			const Dev &d = nl.devs[k];
@@ -542,12 +543,12 @@ struct Flattener {
 				const bool hasTa = d.sets[0].ta && *d.sets[0].ta && d.sets[0].taLen && *d.sets[0].taLen > 0;
 				for (size_t s = 0; s < d.sets.size(); s++) {
 					int id;
-					if (!table(d.sets[s].vi, d.sets[s].viLen, d.viType, id)) return false;
+					if (!table(d.sets[s].vi, d.sets[s].viLen, d.viType, id, 0)) return false;
 					if (s == 0) viTab = id;
 				}
 				for (size_t s = 0; hasTa && s < d.sets.size(); s++) {
 					int id;
-					if (!table(d.sets[s].ta, d.sets[s].taLen, d.taType, id)) {
+					if (!table(d.sets[s].ta, d.sets[s].taLen, d.taType, id, 1)) {
 						err = "every table set of " + d.refdes + " needs a TA table";
 						return false;
 					}

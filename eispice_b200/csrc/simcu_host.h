@@ -77,6 +77,7 @@ struct Program {
 	std::vector<int> calcOff, calcCode, calcVarOff, calcVars;
 	std::vector<double> calcConst;
 	std::vector<int> tabOff, tabType;
+	std::vector<int> tabClass;                    /* 0 V-I table (looked up every Newton iteration), 1 TA, 2 source */
 	std::vector<double> tabP;                     /* [point][4] = x, y, m, x_next */
 	std::vector<int> histRows;
 	std::vector<int> pmap; std::vector<double> pconst;

@@ -38,6 +38,9 @@
 #ifndef SIMCU_WINDOWS
 #define SIMCU_WINDOWS 0
 #endif
+#ifndef SIMCU_SMEMTAB
+#define SIMCU_SMEMTAB 0
+#endif
 
 /* statistics and status of a finished (or failed) instance; the data of an
  * instance with status != 0 is NaN from the failure time on */
@@ -73,6 +76,18 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 {
 	/* a.lanes < 32 spreads a batch that is too small to fill the machine over
 	 * more warps (fewer instances per warp) */
+#if SIMCU_SMEMTAB
+	/* IBIS tables in shared memory (north_star): every block stages the tables the
+	 * Newton loop looks up - one coalesced copy, then per-thread interpolation
+	 * reads them at shared-memory latency instead of competing with the spilled
+	 * state for L1 */
+	{
+		const double2 *src = reinterpret_cast<const double2 *>(a.tabStage);
+		double2 *dst = reinterpret_cast<double2 *>(simcuSmemTab);
+		for (int i = threadIdx.x; i < 2 * a.stagePoints; i += blockDim.x) dst[i] = __ldg(&src[i]);
+		__syncthreads();
+	}
+#endif
 	const int lane = threadIdx.x & 31;
 	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (lane >= a.lanes) return;

@@ -124,6 +124,10 @@ typedef struct {
 	const int *tabOff;        /* [ntab+1] */
 	const int *tabType;       /* 'l' / 'c' */
 	const double *tabP;       /* packed tables: [point][4] = x, y, m, x_next */
+	const int *tabDesc;       /* [ntab][4]: first point, points, type 'l'/'c', first point of the
+	                           * copy staged in shared memory (-1: not staged) */
+	const double *tabStage;   /* the staged tables, contiguous, in shared-memory order */
+	int stagePoints;          /* points staged (32 B each) */
 	const int *histRows;      /* [nh] row index (1-based) recorded per step */
 	int nh, histRecords;
 	const int *probeRows;     /* [nprobes] row index (1-based) */

@@ -157,6 +157,9 @@ int simcuSetInstanceWindow(simcu_ *r, const double *tstep, const double *tstop, 
  * once, 0 = whole warps start together), block_sync (1: the warps of a block
  * start every attempt together and share instruction-cache lines),
  * growth_limit (LU multiplier magnitude counted as pivot growth, default 1e6),
+ * smem_tables_kb (0..200: every block stages that many kB of tables in shared
+ * memory, V-I tables first; big-block launch shapes only; -1 = automatic: 100 kB
+ * for the 256-thread shape, none for the 896-thread shape),
  * tline_prefetch (1: extra locate + L2 prefetch pass over the T-lines; measured
  * slower, off), fmad (default 0: the kernel is compiled WITHOUT a*b+c
  * contraction, i.e. with the reference's arithmetic - under the same pivot
