@@ -7,6 +7,7 @@
  */
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nvrtc.h>
 
 #include <cstdio>
@@ -111,8 +112,43 @@ JitKernel::~JitKernel()
 	if (library) cudaLibraryUnload((cudaLibrary_t)library);
 }
 
+namespace {
+
+/* Optional cubin cache on disk (environment variable SIMCU_CACHE_DIR, off when
+ * unset): NVRTC takes 1-7 s per topology, which a process pays again every time
+ * it starts.  The key is the whole translation unit, the contraction flag and
+ * the build stamp of this library. */
+std::string cachePathOf(const std::string &source, bool fmad)
+{
+	const char *dir = std::getenv("SIMCU_CACHE_DIR");
+	if (!dir || !*dir) return std::string();
+	unsigned long long h = 1469598103934665603ULL;
+	const std::string stamp = std::string(__DATE__ " " __TIME__) + (fmad ? " fmad" : " nofmad");
+	for (size_t i = 0; i < source.size(); i++) { h ^= (unsigned char)source[i]; h *= 1099511628211ULL; }
+	for (size_t i = 0; i < stamp.size(); i++) { h ^= (unsigned char)stamp[i]; h *= 1099511628211ULL; }
+	char name[64];
+	std::snprintf(name, sizeof name, "/simcu_%016llx_%zu.cubin", h, source.size());
+	return std::string(dir) + name;
+}
+
+}  /* namespace */
+
 bool jitCompile(const std::string &source, JitKernel &k, std::string &err, bool fmad)
 {
+	const std::string cached = cachePathOf(source, fmad);
+	if (!cached.empty()) {
+		if (FILE *f = std::fopen(cached.c_str(), "rb")) {
+			std::fseek(f, 0, SEEK_END);
+			const long n = std::ftell(f);
+			std::fseek(f, 0, SEEK_SET);
+			if (n > 0) {
+				k.cubin.resize((size_t)n);
+				if (std::fread(k.cubin.data(), 1, (size_t)n, f) != (size_t)n) k.cubin.clear();
+			}
+			std::fclose(f);
+			if (!k.cubin.empty()) { k.log = "cubin from " + cached; return true; }
+		}
+	}
 	if (!openNvrtc(err)) return false;
 	std::string name = "simcu_topology.cu";
 	if (const char *dir = std::getenv("SIMCU_JIT_DUMP")) {
@@ -143,6 +179,16 @@ bool jitCompile(const std::string &source, JitKernel &k, std::string &err, bool 
 	k.cubin.resize(n);
 	gNvrtc.getCubin(prog, k.cubin.data());
 	gNvrtc.destroyProgram(&prog);
+	if (!cached.empty()) {          /* write-then-rename: concurrent ranks compile the same source */
+		char tmp[32];
+		std::snprintf(tmp, sizeof tmp, ".%ld.tmp", (long)getpid());
+		const std::string part = cached + tmp;
+		if (FILE *f = std::fopen(part.c_str(), "wb")) {
+			const bool ok = std::fwrite(k.cubin.data(), 1, k.cubin.size(), f) == k.cubin.size();
+			std::fclose(f);
+			if (!ok || std::rename(part.c_str(), cached.c_str()) != 0) std::remove(part.c_str());
+		}
+	}
 	return true;
 }
 

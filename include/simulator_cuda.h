@@ -311,7 +311,11 @@ int simcuFetchRaw(simcu_ *r, int instance, double *data[], int *numPoints,
 int simcuFetchRawBlock(simcu_ *r, double *out, int *numPoints);
 
 /* ---- introspection (host only, no GPU needed) ----------------------------- */
-/* path and version of the NVRTC library the kernels were compiled with ("" before
+/* Environment: SIMCU_NVRTC / SIMCU_NCCL = library paths; SIMCU_JIT_DUMP = a
+ * directory that receives every generated translation unit; SIMCU_CACHE_DIR = a
+ * directory used as a cubin cache across processes (NVRTC takes 1-7 s per
+ * topology; off when unset).
+ * path and version of the NVRTC library the kernels were compiled with ("" before
  * the first compile).  The toolkit's own copy is preferred over one a host
  * application (PyTorch) has already loaded; override with SIMCU_NVRTC. */
 const char *simcuNvrtcPath(void);

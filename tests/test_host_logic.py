@@ -535,3 +535,23 @@ def test_windows_and_source_table_sets_compile_without_a_gpu():
     src, _ = eng.compile_only(["v(out)"])
     assert "#define SIMCU_WINDOWS 0" in src
     eng.close()
+
+
+def test_cubin_cache_on_disk(tmp_path, monkeypatch):
+    """SIMCU_CACHE_DIR: the second compile of a topology (any process) reads the
+    cubin back instead of running NVRTC again."""
+    import time
+    monkeypatch.setenv("SIMCU_CACHE_DIR", str(tmp_path))
+    w_nl = circuits.all_cases()["cfg4_ibis"][0]().netlist()
+    t = []
+    sizes = []
+    for _ in range(2):
+        eng = engine.Engine(w_nl, 4)
+        t0 = time.time()
+        src, n = eng.compile_only(["v(vo)"])
+        t.append(time.time() - t0)
+        sizes.append(n)
+        eng.close()
+    files = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(files) == 1 and sizes[0] == sizes[1] == os.path.getsize(os.path.join(tmp_path, files[0]))
+    assert t[1] < 0.5 * t[0], t
