@@ -18,6 +18,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -460,7 +461,7 @@ int simcuSetInstanceParam(simcu_ *r, char *refdes, char *name, const double *val
 	case DK_R: ok = (n == "R"); break;
 	case DK_C: ok = (n == "C"); break;
 	case DK_L: ok = (n == "L"); break;
-	case DK_T: ok = (n == "Z0" || n == "Td" || n == "loss"); break;
+	case DK_T: ok = (n == "Z0" || n == "Td" || n == "loss" || n == "bypass"); break;
 	case DK_V: case DK_I:
 		ok = (n == "DC") || (n.size() == 2 && n[0] == 'A' && n[1] >= '0' && n[1] <= '6' &&
 				d->wtype && d->wtype != 'l' && d->wtype != 'c');
@@ -791,9 +792,29 @@ int analyseFrom(simcu_ *r, int ph, const DBuf &dA, int P)
 int pilotPass(simcu_ *r, bool needOP, bool needTran)
 {
 	const Program &p = r->prog;
-	const int M = r->M, P = std::min(M, r->numPilots);
+	const int M = r->M;
+	int P = std::min(M, r->numPilots);
 	std::vector<int> idx(P);
 	for (int q = 0; q < P; q++) idx[q] = (P > 1) ? (int)((long long)q * (M - 1) / (P - 1)) : 0;
+	/* every value of a categorical column (IBIS table set, T-line bypass flag) must
+	 * be seen by the analysis: one fixed sequence has to serve all of them */
+	{
+		const size_t cap = 64;
+		for (int k = 0; k < p.niinst && idx.size() < cap; k++) {
+			std::set<int> seen;
+			for (size_t q = 0; q < idx.size(); q++) seen.insert(p.iinst[(size_t)k * M + idx[q]]);
+			for (int i = 0; i < M && idx.size() < cap; i++)
+				if (seen.insert(p.iinst[(size_t)k * M + i]).second) idx.push_back(i);
+		}
+		for (size_t c = 0; c < p.catInst.size() && idx.size() < cap; c++) {
+			const size_t k = (size_t)p.catInst[c];
+			std::set<double> seen;
+			for (size_t q = 0; q < idx.size(); q++) seen.insert(p.pinst[k * M + idx[q]]);
+			for (int i = 0; i < M && idx.size() < cap; i++)
+				if (seen.insert(p.pinst[k * M + i]).second) idx.push_back(i);
+		}
+		P = (int)idx.size();
+	}
 	std::vector<double> pin((size_t)p.ninst * P);
 	std::vector<int> iin((size_t)p.niinst * P);
 	for (int k = 0; k < p.ninst; k++)

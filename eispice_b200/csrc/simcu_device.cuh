@@ -878,6 +878,19 @@ DEV void devLoad(Inst &c, const int *d, const int *bv = nullptr)
 		for (int k = 0; k < 6; k++) c.S(sb + k) = 0.0;
 		const int *s = d + DF_TA0;
 		/* RK RJ KR JR RL RM SL SM LS MS SK SJ RR SS KS JS LR MR */
+		if (d[DF_PBYPASS] >= 0 && c.P(d[DF_PBYPASS]) != 0.0) {
+			/* masked section of a maximum topology (not in the
+			 * reference): the two ports are joined by an ideal 0 V branch -
+			 * V_K - V_J = V_L - V_M, the branch current i(ref#in1) flows through
+			 * both, i(ref#in2) = 0 - at the operating point and in transient */
+			c.Aset(s[0], 1.0); c.Aset(s[1], -1.0); c.Aset(s[4], -1.0); c.Aset(s[5], 1.0);
+			c.Aset(s[2], 1.0); c.Aset(s[3], -1.0); c.Aset(s[16], -1.0); c.Aset(s[17], 1.0);
+			c.Aset(s[6], 0.0); c.Aset(s[7], 0.0); c.Aset(s[8], 0.0); c.Aset(s[9], 0.0);
+			c.Aset(s[10], 0.0); c.Aset(s[11], 0.0); c.Aset(s[14], 0.0); c.Aset(s[15], 0.0);
+			c.Aplus(s[13], 1.0);
+			c.S(sb + 24) = 1.0;
+			break;
+		}
 		c.Aset(s[4], -1.0); c.Aset(s[5], 1.0); c.Aset(s[10], -1.0); c.Aset(s[11], 1.0);
 		c.Aset(s[14], 1.0); c.Aset(s[15], -1.0); c.Aset(s[16], -1.0); c.Aset(s[17], 1.0);
 		c.Aset(s[0], 1.0); c.Aset(s[1], -1.0); c.Aset(s[2], 1.0); c.Aset(s[3], -1.0);
@@ -994,6 +1007,7 @@ DEV void devInitStep(Inst &c, const int *d)
 		break;
 	case DK_T: {                                /* tline.c:93-122 */
 		const int *s = d + DF_TA0;
+		if (d[DF_PBYPASS] >= 0 && c.P(d[DF_PBYPASS]) != 0.0) break;
 		c.Aset(s[4], 0.0); c.Aset(s[5], 0.0); c.Aset(s[10], 0.0); c.Aset(s[11], 0.0);
 		c.Aset(s[14], 0.0); c.Aset(s[15], 0.0); c.Aset(s[16], 0.0); c.Aset(s[17], 0.0);
 		c.S(sb + 2) = c.X(d[DF_K]); c.S(sb + 3) = c.X(d[DF_J]);
@@ -1128,6 +1142,7 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 		return cbIsBreak(c, sb + 4, ib + 1, aa, k.maxAngleA);
 	}
 	case DK_T: {                                /* tline.c:126-204 */
+		if (d[DF_PBYPASS] >= 0 && c.P(d[DF_PBYPASS]) != 0.0) return 0;
 		const double tp = c.time - c.P(d[DF_PTD]);
 		if (isnan(tp)) { c.err = SIMCU_ERR_NAN; return 0; }
 		double Ir, Is, Vk, Vj, Vl, Vm;

@@ -435,6 +435,7 @@ struct Flattener {
 		const int pid = (int)p.pmap.size();
 		std::map<std::string, std::vector<double> >::const_iterator it = d.inst.find(name);
 		if (it != d.inst.end()) {
+			if (!std::strcmp(name, "bypass")) p.catInst.push_back(p.ninst);
 			p.pmap.push_back(p.ninst);
 			p.pconst.push_back(0.0);
 			p.pinst.insert(p.pinst.end(), it->second.begin(), it->second.end());
@@ -491,7 +492,7 @@ struct Flattener {
 	/* parameters and tables, in device order; fills rec when it is given */
 	bool parameters(bool writeRecords)
 	{
-		p.pmap.clear(); p.pconst.clear(); p.pinst.clear(); p.iinst.clear();
+		p.pmap.clear(); p.pconst.clear(); p.pinst.clear(); p.iinst.clear(); p.catInst.clear();
 		p.ninst = 0; p.niinst = 0;
 		p.tabOff.assign(1, 0); p.tabType.clear(); p.tabClass.clear();
 		p.tabP.clear();
@@ -537,6 +538,10 @@ struct Flattener {
 			case DK_T:
 				a = param(d, "Z0", d.z0); b = param(d, "Td", d.td); c = param(d, "loss", d.loss);
 				if (rec) { rec[DF_PZ0] = a; rec[DF_PTD] = b; rec[DF_PLOSS] = c; }
+				if (d.inst.count("bypass")) {      /* masked maximum topology: per-instance flag */
+					const int m = param(d, "bypass", nullptr);
+					if (rec) rec[DF_PBYPASS] = m;
+				}
 				break;
 			case DK_VI: {
 				int viTab = -1, taTab = -1;
@@ -661,11 +666,14 @@ struct Flattener {
 				static const char inTran[18] = {1, 1, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 1, 1, 0, 0, 0, 0};
 				/* devLoad (tline.c:236-267) and devInitStep (:104-111) literals */
 				static const double atOP[18] = {1, -1, 1, -1, -1, 1, 1, -1, 1, -1, -1, 1, 0, 0, 1, -1, -1, 1};
+				/* a section that some instances bypass (ideal through-connection, see
+				 * devLoad) keeps all 18 entries in both patterns, none of them a literal */
+				const bool maskable = d.inst.count("bypass") != 0;
 				for (int j = 0; j < 18; j++) {
 					rec[DF_TA0 + j] = s[j];
 					mark(p.activeOP, s[j]);
-					if (inTran[j]) mark(p.activeTran, s[j]);
-					if (j == 12 || j == 13) ref(s[j]);          /* RR, SS = -Z0 */
+					if (inTran[j] || maskable) mark(p.activeTran, s[j]);
+					if (j == 12 || j == 13 || maskable) ref(s[j]);          /* RR, SS = -Z0 */
 					else lit(s[j], atOP[j], inTran[j] ? atOP[j] : 0.0);
 				}
 				const int rows[6] = {R, S, K, J, L, Mm};

@@ -84,6 +84,7 @@ struct Program {
 	std::vector<double> pinst;                    /* [ninst][M] */
 	std::vector<int> iinst;                       /* [niinst][M] */
 	int ninst = 0, niinst = 0;
+	std::vector<int> catInst;                     /* pinst columns that are flags (T-line bypass): pilots cover every value */
 	int stateDoubles = 0, stateInts = 0;
 	std::vector<char> activeOP, activeTran;       /* [nnzA] slot can be non-zero */
 	/* slots that hold the same compile-time constant for every instance in a

@@ -44,6 +44,7 @@ enum {
 #define DF_PLOSS   11
 #define DF_TA0     12    /* RK RJ KR JR RL RM SL SM LS MS SK SJ RR SS KS JS LR MR */
 #define DF_TH0     30    /* history column of R S K J L M (-1 = ground) */
+#define DF_PBYPASS 36    /* parameter id of the per-instance bypass flag, -1: never bypassed */
 /* VI */
 #define DF_VITAB   9
 #define DF_TATAB   10    /* -1: no TA table */

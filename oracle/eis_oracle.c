@@ -963,6 +963,7 @@ typedef struct {
 	/* parameters (by value; the reference holds pointers) */
 	double val;                  /* R, C, L, DC */
 	double Z0, Td, loss;
+	int bypass;             /* engine extension under test: the section is an ideal through-connection */
 	/* state */
 	double G, Ieq;               /* C: G,Ieq  L: R,Veq  VI: G,Ieq  BC: cap G,Ieq */
 	double a;                    /* VI multiplier */
@@ -1352,6 +1353,7 @@ int eoSetParam(eo_sim *s, const char *refdes, const char *name, double v)
 		if (!strcmp(name, "Z0")) { d->Z0 = v; return 0; }
 		if (!strcmp(name, "Td")) { d->Td = v; return 0; }
 		if (!strcmp(name, "loss")) { d->loss = v; return 0; }
+		if (!strcmp(name, "bypass")) { d->bypass = (v != 0.0); return 0; }
 		if (name[0] == 'A' && name[1] >= '0' && name[1] <= '6' && !name[2] &&
 				d->wave) { d->wave->arg[name[1] - '0'] = v; return 0; }
 		FAIL("unknown parameter %s.%s", refdes, name);
@@ -1474,6 +1476,17 @@ static int devLoad(eo_sim *s, Dev *d)
 		d->hint = 0;
 		d->Vr = 0.0; d->Vs = 0.0;
 		for (i = 0; i < 6; i++) d->ic[i] = 0.0;
+		if (d->bypass) {
+			/* masked section (not in the reference; mirrors simcu_device.cuh): the
+			 * two ports are joined by an ideal 0 V branch, V_K - V_J = V_L - V_M with
+			 * the branch current i(ref#in1) through both; i(ref#in2) = 0 */
+			aSet(s, R, L, -1.0); aSet(s, R, M, 1.0); aSet(s, S, K, 0.0); aSet(s, S, J, 0.0);
+			aSet(s, K, S, 0.0); aSet(s, J, S, 0.0); aSet(s, L, R, -1.0); aSet(s, M, R, 1.0);
+			aSet(s, R, K, 1.0); aSet(s, R, J, -1.0); aSet(s, K, R, 1.0); aSet(s, J, R, -1.0);
+			aSet(s, S, L, 0.0); aSet(s, S, M, 0.0); aSet(s, L, S, 0.0); aSet(s, M, S, 0.0);
+			aPlus(s, S, S, 1.0);
+			break;
+		}
 		aSet(s, R, L, -1.0); aSet(s, R, M, 1.0); aSet(s, S, K, -1.0); aSet(s, S, J, 1.0);
 		aSet(s, K, S, 1.0); aSet(s, J, S, -1.0); aSet(s, L, R, -1.0); aSet(s, M, R, 1.0);
 		aSet(s, R, K, 1.0); aSet(s, R, J, -1.0); aSet(s, K, R, 1.0); aSet(s, J, R, -1.0);
@@ -1578,6 +1591,7 @@ static int devInitStep(eo_sim *s, Dev *d)
 	case D_T: {                                 /* tline.c:93-122 */
 		int K = d->pin[0], J = d->pin[1], L = d->pin[2], M = d->pin[3];
 		int R = d->rowR, S = d->rowS;
+		if (d->bypass) return 0;
 		aSet(s, R, L, 0.0); aSet(s, R, M, 0.0); aSet(s, S, K, 0.0); aSet(s, S, J, 0.0);
 		aSet(s, K, S, 0.0); aSet(s, J, S, 0.0); aSet(s, L, R, 0.0); aSet(s, M, R, 0.0);
 		d->ic[0] = 0.0; d->ic[1] = 0.0;
@@ -1642,6 +1656,7 @@ static int devStep(eo_sim *s, Dev *d, int *brk)
 	}
 	case D_T: {                                 /* tline.c:126-204 */
 		double tp = c->time - d->Td, Ir, Is, Vk, Vj, Vl, Vm, Vr, Vs;
+		if (d->bypass) return 0;
 		if (isnan(tp)) FAIL("T-line: NaN");
 		if (tp <= 0) {
 			Ir = d->ic[0]; Is = d->ic[1]; Vk = d->ic[2]; Vj = d->ic[3];

@@ -186,3 +186,38 @@ def algorithmic_bytes(stats, n_tlines, n_outputs):
                     stats["stateDoubles"])
     H = 18 * n_tlines
     return 8.0 * (k * (nnz + 2 * F + 2 * N) + 2 * (nnz + N) + 2 * S + H + n_outputs), k
+
+
+def cfg5_masked(M, seed=20266, max_sections=8):
+    """the cfg5 link as a MAXIMUM topology of 8 sections, of
+    which instance i uses only n_i = 1 + i % 8 - the others are bypassed
+    ("Tk.bypass" = 1: an ideal through-connection).  One topology, one kernel."""
+    w = cfg5(M, seed)
+    n_active = 1 + (np.arange(M) % max_sections)
+    for k in range(1, max_sections + 1):
+        w.params["T%d.bypass" % k] = (k > n_active).astype(np.float64)
+    w.name = "cfg5_masked"
+    w.n_active = n_active
+    return w
+
+
+def reduced_link_netlist(w, i):
+    """Instance i of cfg5_masked as the REDUCED topology the reference can run:
+    the link built with only its n_i active sections, same parameters."""
+    n = int(w.n_active[i])
+    cct = _ibis_link(n)
+    full = {k: v[i] for k, v in w.params.items()}
+    vi_set = int(full[[k for k in full if k.endswith(".set")][0]])
+    out = []
+    for d in cct.netlist():
+        d = list(d)
+        k, ref = d[0], d[1]
+        if k in ("R", "C", "L") and "%s.%s" % (ref, k) in full:
+            d[4] = float(full["%s.%s" % (ref, k)])
+        elif k == "T":
+            for j, m in enumerate(("Z0", "Td", "loss")):
+                d[6 + j] = float(full["%s.%s" % (ref, m)])
+        elif k in ("V", "I") and "%s.DC" % ref in full:
+            d[5] = float(full["%s.DC" % ref])
+        out.append(tuple(d))
+    return out, vi_set
