@@ -121,7 +121,12 @@ int simcuAddTLineW(simcu_ *r, char *refdes, char *nodes[], int nNodes, int *M,
 /* ---- the instance dimension (additive) ----------------------------------- */
 /* Per-instance values of a scalar parameter: name is the binding's member name
  * (R C L DC Z0 Td loss, or A0..A6 = waveform argument slot).  values[i*stride]
- * is instance i; stride 0 broadcasts.  Copied immediately. */
+ * is instance i; stride 0 broadcasts.  Copied immediately.
+ * T-lines also take "bypass" (0 / 1): a per-instance TOPOLOGY flag - where it is
+ * 1 the section is an ideal through-connection (V_K - V_J = V_L - V_M, the same
+ * current through both ports), at the operating point and in transient, so a
+ * sweep over the number of sections of a line runs as one batch of the maximum
+ * topology. */
 int simcuSetInstanceParam(simcu_ *r, char *refdes, char *name,
 		const double *values, int stride);
 /* Further table sets (e.g. IBIS corners) for an existing VI device; returns
