@@ -141,7 +141,7 @@ struct _simcu {
 	int smemTablesKB = -1;          /* budget for that (option smem_tables_kb; 0 = tables stay global, -1 = automatic) */
 	int smemTablesUsed = 0;
 	DBuf dDev, dBvar, dLu[2], dXslot[2], dCalcOff, dCalcCode, dCalcConst,
-		dCalcVarOff, dCalcVars, dTabOff, dTabType, dTabP, dHistRows,
+		dCalcVarOff, dCalcVars, dTabP, dHistRows,
 		dProbeRows, dPmap, dPconst, dPinst, dIinst, dOrder, dOrder2, dMeasure, dMeasureLevel,
 		dReplayOff, dReplayTime, dReplayFlag, dReplayLinOff, dReplayLin, dWin;
 	DBuf dA, dB, dX, dS, dIS, dCD, dCI, dHt, dHx, dOutGrid, dOutT, dStatusT, dOutRaw, dWs, dRemaining;
@@ -162,7 +162,7 @@ struct _simcu {
 	~_simcu()
 	{
 		DBuf *all[] = {&dDev, &dBvar, &dLu[0], &dLu[1], &dXslot[0], &dXslot[1], &dCalcOff,
-			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabOff, &dTabType, &dTabP, &dOrder, &dOrder2, &dMeasure,
+			&dCalcCode, &dCalcConst, &dCalcVarOff, &dCalcVars, &dTabP, &dOrder, &dOrder2, &dMeasure,
 			&dMeasureLevel, &dReplayOff, &dReplayTime, &dReplayFlag, &dReplayLinOff, &dReplayLin, &dWin, &dTabDesc, &dTabStage, &dHistRows, &dProbeRows, &dPmap, &dPconst, &dPinst, &dIinst,
 			&dA, &dB, &dX, &dS, &dIS, &dCD, &dCI, &dHt, &dHx, &dOutGrid, &dOutT, &dStatusT, &dOutRaw,
 			&dWs, &dRemaining};
@@ -651,7 +651,6 @@ int uploadParameters(simcu_ *r, cudaStream_t st)
 	const Program &p = r->prog;
 	if (r->dPmap.upload(p.pmap, st) || r->dPconst.upload(p.pconst, st) ||
 			r->dPinst.upload(p.pinst, st) || r->dIinst.upload(p.iinst, st) ||
-			r->dTabOff.upload(p.tabOff, st) || r->dTabType.upload(p.tabType, st) ||
 			r->dTabP.upload(p.tabP, st))
 		return -1;
 	/* table descriptors, and the tables every block stages in shared memory: V-I
@@ -701,7 +700,6 @@ int uploadParameters(simcu_ *r, cudaStream_t st)
 		a.order = order;
 		a.pmap = r->dPmap.as<int>(); a.pconst = r->dPconst.as<double>();
 		a.pinst = r->dPinst.as<double>(); a.iinst = r->dIinst.as<int>();
-		a.tabOff = r->dTabOff.as<int>(); a.tabType = r->dTabType.as<int>();
 		a.tabP = r->dTabP.as<double>();
 		a.tabDesc = r->dTabDesc.as<int>(); a.tabStage = r->dTabStage.as<double>();
 		a.stagePoints = r->stagePoints;

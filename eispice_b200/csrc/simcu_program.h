@@ -122,8 +122,6 @@ typedef struct {
 	const double *calcConst;
 	const int *calcVarOff;    /* [ncalc+1] offsets into calcVars */
 	const int *calcVars;      /* row index (0 = ground), CALC_VAR_TIME */
-	const int *tabOff;        /* [ntab+1] */
-	const int *tabType;       /* 'l' / 'c' */
 	const double *tabP;       /* packed tables: [point][4] = x, y, m, x_next */
 	const int *tabDesc;       /* [ntab][4]: first point, points, type 'l'/'c', first point of the
 	                           * copy staged in shared memory (-1: not staged) */
