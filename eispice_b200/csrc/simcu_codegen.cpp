@@ -563,6 +563,41 @@ void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vec
 	o.f("\tif (bad) c.err = SIMCU_ERR_SINGULAR;\n\tif (grow) c.growth++;\n}\n\n");
 }
 
+/* The last accepted solution (matrixRecall, core/matrix.c:385-392) is only ever
+ * read - between a rejected attempt and the next solve, or as the "previous
+ * point" of the output interpolation - at the rows the step / integrate phases
+ * and the probes use: C / L / nonlinear-C terminals, the variables of
+ * time-dependent B sources, probe and measure rows.  Only those are saved on
+ * accept and restored on reject (cfg5: 10 of 48 unknowns). */
+void emitSaveRecall(Out &o, const Program &p, const std::vector<int> &probeRows,
+		const std::vector<int> &measures)
+{
+	std::vector<char> need(p.N + 1, 0);
+	for (int k = 0; k < p.ndev; k++) {
+		const int *rec = &p.dev[(size_t)k * SIMCU_DEV_STRIDE];
+		const int kind = rec[DF_TYPE];
+		const bool bsrc = (kind == DK_BI || kind == DK_BV || kind == DK_BC);
+		if (kind == DK_C || kind == DK_BC) { need[rec[DF_K]] = 1; need[rec[DF_J]] = 1; }
+		if (kind == DK_L) need[rec[DF_ROWR]] = 1;
+		if (bsrc && rec[DF_USETIME]) {
+			need[rec[DF_K]] = 1; need[rec[DF_J]] = 1; need[rec[DF_ROWR]] = 1;
+			if (rec[DF_ROWM] > 0) need[rec[DF_ROWM]] = 1;
+			for (int j = 0; j < rec[DF_NBV]; j++) need[p.bvar[(size_t)4 * (rec[DF_BVOFF] + j)]] = 1;
+			const int id = rec[DF_CALC];
+			for (int v = p.calcVarOff[id]; v < p.calcVarOff[id + 1]; v++)
+				if (p.calcVars[v] > 0) need[p.calcVars[v]] = 1;
+		}
+	}
+	for (size_t j = 0; j < probeRows.size(); j++) need[probeRows[j]] = 1;
+	for (size_t q = 0; 2 * q + 1 < measures.size(); q++) need[measures[2 * q + 1]] = 1;
+	o.f("DEV void genSaveX(const Inst &c)\n{\n");
+	for (int r = 1; r <= p.N; r++) if (need[r]) o.f("\tc.Xa[%d] = c.Xv[%d];\n", r - 1, r - 1);
+	o.f("\t(void)c;\n}\n\n");
+	o.f("DEV void genRecallX(const Inst &c)\n{\n");
+	for (int r = 1; r <= p.N; r++) if (need[r]) o.f("\tc.Xv[%d] = c.Xa[%d];\n", r - 1, r - 1);
+	o.f("\t(void)c;\n}\n\n");
+}
+
 void emitRows(Out &o, const char *name, const std::vector<int> &rows)
 {
 	o.f("DEV void %s(int *rows)\n{\n", name);
@@ -611,6 +646,7 @@ std::string generateTopology(const Program &p, const Schedule sched[2],
 	emitPhases(o, p, tlinePrefetch);
 	emitFactorSolve(o, p, sched[0], active[0], consts[0], 0, growthGuard);
 	emitFactorSolve(o, p, sched[1], active[1], consts[1], 1, growthGuard);
+	emitSaveRecall(o, p, probeRows, measures);
 	emitRows(o, "genHistRows", p.histRows);
 	emitRows(o, "genProbeRows", probeRows);
 	/* measures: (kind, row) pairs; the level comes from the kernel arguments */

@@ -261,8 +261,7 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 			else {
 				gridOutput(c, prows, 0.0, 0.0, true);
 				genMeasures(c, meas, 0.0, 0.0, true);
-				SIMCU_UNROLL
-				for (int r = 0; r < SIMCU_N; r++) c.Xa[r] = c.Xv[r];
+				genSaveX(c);
 				if (opOnly || !(0.0 < W_TSTOP(c))) { recordStep(c, hrows, 0.0); done = true; }
 				else {
 					genInitStep(c);
@@ -301,8 +300,7 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 			} else if (outcome == 0) {                      /* accepted: :220-233 */
 				gridOutput(c, prows, prevTime, time, false);
 				genMeasures(c, meas, prevTime, time, false);
-				SIMCU_UNROLL
-				for (int r = 0; r < SIMCU_N; r++) c.Xa[r] = c.Xv[r];
+				genSaveX(c);
 				order = (order < k.maxorder) ? order + 1 : order;
 				prevTime = time;
 				if (brk) maxStep = Min3(lteStep, 0.1 * maxStep, W_TMAX(c));
@@ -324,9 +322,9 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 				}
 			}
 			if (!done && outcome != 0) {
-				/* matrixRecall (:217): back to the last accepted solution */
-				SIMCU_UNROLL
-				for (int r = 0; r < SIMCU_N; r++) c.Xv[r] = c.Xa[r];
+				/* matrixRecall (:217): back to the last accepted solution - at the
+				 * rows anything reads before the next solve overwrites X */
+				genRecallX(c);
 			}
 #if SIMCU_REPLAY
 			if (!done && rp >= rpEnd) done = true;
