@@ -120,6 +120,8 @@ struct _simcu {
 	double growthLimit = 1e6;       /* LU multiplier magnitude that counts as pivot growth */
 	int tlinePrefetch = 0;          /* locate + prefetch pass over the T-lines (>= 2 lines): measured slower */
 	int fmad = 0;                   /* 0: no a*b+c contraction - the reference's arithmetic (default) */
+	int solveBlocks = 2;            /* generated LU: 0 all at once, 1 block by block, 2 + invariant blocks once per Newton loop */
+	int sharedCb = 1;               /* one break-point clock per instance */
 	std::vector<int> replayOff, replayFlag, replayLinOff, replayLin;
 	std::vector<double> winTstep, winTstop, winTmax;   /* per-instance analysis windows (empty: one window) */
 	std::vector<double> replayTime;
@@ -567,6 +569,8 @@ int simcuSetOption(simcu_ *r, char *name, double value)
 	else if (n == "growth_limit") r->growthLimit = value;
 	else if (n == "tline_prefetch") r->tlinePrefetch = (value != 0.0);
 	else if (n == "fmad") r->fmad = (value != 0.0);
+	else if (n == "solve_blocks") r->solveBlocks = std::max(0, std::min(2, (int)value));
+	else if (n == "shared_break_clock") r->sharedCb = (value != 0.0);
 	else return fail("unknown option %s", name);
 	r->prepared = false;
 	return 0;
@@ -878,6 +882,7 @@ int buildJitKernel(simcu_ *r)
 	cfg.replay = r->replay; cfg.blockSync = r->blockSyncUsed; cfg.syncGroup = r->syncGroup;
 	cfg.windows = !r->winTstep.empty(); cfg.growthLimit = r->growthLimit; cfg.tlinePrefetch = r->tlinePrefetch; cfg.fmad = r->fmad;
 	cfg.smemTab = (r->stagePoints > 0);
+	cfg.solveBlocks = r->solveBlocks; cfg.sharedCb = r->sharedCb;
 	if (r->jit && r->jitProbes == r->probeRows && r->jitCfg == cfg && r->jitMeasures == r->measures)
 		return 0;
 	const std::string src = assembleSource(r->prog, r->sched, r->active, r->consts, r->probeRows,
@@ -1650,6 +1655,7 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	cfg.threadsPerBlock = tpb; cfg.minBlocks = r->minBlocks; cfg.gmin = r->ctl.gmin; cfg.replay = r->replay;
 	cfg.blockSync = (r->blockSync > 0); cfg.syncGroup = r->syncGroup; cfg.growthLimit = r->growthLimit;
 	cfg.windows = !r->winTstep.empty(); cfg.fmad = r->fmad; cfg.smemTab = (r->smemTablesKB > 0); cfg.tlinePrefetch = r->tlinePrefetch;
+	cfg.solveBlocks = r->solveBlocks; cfg.sharedCb = r->sharedCb;
 	const std::string src = assembleSource(p, sched, active, consts, probeRows, r->measures, cfg);
 	if (source) *source = strdup(src.c_str());
 	JitKernel k;

@@ -447,7 +447,17 @@ bool inPhase(const int *rec, int phase)
 	}
 }
 
-void emitPhases(Out &o, const Program &p, bool tlinePrefetch)
+/* devices whose step phase runs the break-point test (checkbreak.c:43-67) */
+bool stepHasBreakTest(const int *rec)
+{
+	const int kind = rec[DF_TYPE];
+	if ((kind == DK_V || kind == DK_I) && rec[DF_WTYPE] != 0) return true;
+	if (kind == DK_VI && rec[DF_TATAB] >= 0) return true;
+	if (kind == DK_T) return true;
+	return (kind == DK_BI || kind == DK_BV) && rec[DF_USETIME];
+}
+
+void emitPhases(Out &o, const Program &p, bool tlinePrefetch, bool sharedCb)
 {
 	static const char *const head[7] = {
 		"DEV void genLoad(Inst &c)\n{\n",
@@ -473,6 +483,11 @@ void emitPhases(Out &o, const Program &p, bool tlinePrefetch)
 			for (int k = 0; k < p.ndev; k++) any = any || inPhase(&p.dev[(size_t)k * SIMCU_DEV_STRIDE], 3);
 			if (any) o.f("\titBegin(c);\n");
 		}
+		if (ph == 2 && sharedCb) {    /* step: the shared break-point clock advances once */
+			bool any = false;
+			for (int k = 0; k < p.ndev; k++) any = any || stepHasBreakTest(&p.dev[(size_t)k * SIMCU_DEV_STRIDE]);
+			if (any) o.f("\tcbBegin(c);\n");
+		}
 		if (ph == 2 && tlinePrefetch) {
 			/* step: with several T-lines, a first pass locates every line's delayed
 			 * time and prefetches the records, so their DRAM latencies overlap */
@@ -496,70 +511,163 @@ void emitPhases(Out &o, const Program &p, bool tlinePrefetch)
 }
 
 /* ---- numeric LU + solves, straight-line --------------------------------------- */
+
+/* A slots and right-hand-side rows that the linearize phase can change, i.e.
+ * everything that may differ between two solves of ONE simulatorSolve loop
+ * (core/simulator.c:45-69): the stamps of the V-I curves (vicurve.c:110-163)
+ * and of the B sources (nonlinear_*.c).  Conservative: every slot and row the
+ * record of such a device names. */
+void newtonTouched(const Program &p, std::vector<char> &slot, std::vector<char> &row)
+{
+	slot.assign(p.nnzA, 0);
+	row.assign(p.N + 1, 0);
+	auto markSlot = [&](int sl) { if (sl >= 0 && sl < p.nnzA) slot[sl] = 1; };
+	auto markRow = [&](int r) { if (r >= 1 && r <= p.N) row[r] = 1; };
+	for (int k = 0; k < p.ndev; k++) {
+		const int *rec = &p.dev[(size_t)k * SIMCU_DEV_STRIDE];
+		const int kind = rec[DF_TYPE];
+		const bool bsrc = (kind == DK_BI || kind == DK_BV || kind == DK_BC);
+		if (kind != DK_VI && !bsrc) continue;
+		markRow(rec[DF_K]); markRow(rec[DF_J]); markRow(rec[DF_L]); markRow(rec[DF_M]);
+		markRow(rec[DF_ROWR]); markRow(rec[DF_ROWM]);
+		if (kind == DK_VI) for (int j = 0; j < 8; j++) markSlot(rec[DF_VA0 + j]);
+		else {
+			for (int j = 0; j < 6; j++) markSlot(rec[DF_BA0 + j]);
+			for (int j = 0; j < rec[DF_NBV]; j++) {
+				const int *bv = &p.bvar[(size_t)4 * (rec[DF_BVOFF] + j)];
+				markRow(bv[0]); markSlot(bv[1]); markSlot(bv[2]);
+			}
+		}
+	}
+}
+
+/* The matrix of a circuit with T-lines falls apart into independent blocks (a
+ * line couples its two ports only through the history, i.e. the right-hand side:
+ * tline.c:104-111), and the pivot sequence wanders between them.  `blocks`
+ * regroups the straight-line code block by block - loads, elimination, back
+ * substitution and the stores of one block before the next one starts - so that
+ * only one block's entries are live at a time (at 72 registers per thread the
+ * all-at-once order spills ~90 doubles per solve).  Every operation keeps its
+ * operands and its place among the operations of ITS block, so the results are
+ * bit-identical.  blocks == 2 additionally runs the blocks no linearize stamp
+ * reaches only in the FIRST solve of a Newton loop: their stamps, right-hand
+ * side and therefore solution cannot change before the loop ends (cfg5: the
+ * seven inner nodes of the 8-section line, 21 of 48 unknowns). */
 void emitFactorSolve(Out &o, const Program &p, const Schedule &s, const std::vector<char> &active,
-		const std::vector<double> &cst, int phase, bool guard)
+		const std::vector<double> &cst, int phase, bool guard, int blocks)
 {
 	const int N = p.N, F = s.F;
 	o.f("/* %s: %d unknowns, %d matrix slots (%d fill), %d L + %d U off-diagonal entries */\n",
 			phase ? "transient" : "operating point", N, F, F - p.nnzA, s.nL, s.nU);
-	o.f("DEV void genFactorSolve%d(Inst &c)\n{\n\tbool bad = false, grow = false;\n", phase);
-	/* which slots the schedule touches */
+	/* where each pivot step starts; connected components over slots (0..F-1) and
+	 * right-hand-side entries (F..F+N-1) */
+	std::vector<int> start(N), uf(F + N);
+	for (int v = 0; v < F + N; v++) uf[v] = v;
+	auto find = [&](int v) { while (uf[v] != v) { uf[v] = uf[uf[v]]; v = uf[v]; } return v; };
+	auto join = [&](int a, int b) { a = find(a); b = find(b); if (a != b) uf[(a < b) ? b : a] = (a < b) ? a : b; };
 	std::vector<char> used(F, 0);
 	{
 		int pos = 0;
 		for (int k = 0; k < N; k++) {
-			const int nU = s.lu[pos + 2], nL = s.lu[pos + 3];
-			used[s.lu[pos]] = 1;
-			for (int j = 0; j < nU; j++) used[s.lu[pos + 4 + 2 * j]] = 1;
+			start[k] = pos;
+			const int d = s.lu[pos], yk = s.lu[pos + 1], nU = s.lu[pos + 2], nL = s.lu[pos + 3];
+			used[d] = 1;
+			join(d, yk);
+			for (int j = 0; j < nU; j++) {
+				used[s.lu[pos + 4 + 2 * j]] = 1;
+				join(d, s.lu[pos + 4 + 2 * j]); join(d, s.lu[pos + 4 + 2 * j + 1]);
+			}
 			const int *lrow = &s.lu[pos + 4 + 2 * nU];
 			for (int r = 0; r < nL; r++) {
 				const int *e = lrow + r * (2 + nU);
 				used[e[0]] = 1;
-				for (int j = 0; j < nU; j++) used[e[2 + j]] = 1;
+				join(d, e[0]); join(d, e[1]);
+				for (int j = 0; j < nU; j++) { used[e[2 + j]] = 1; join(d, e[2 + j]); }
 			}
 			pos += 4 + 2 * nU + nL * (2 + nU);
 		}
 	}
-	for (int sl = 0; sl < F; sl++) {
-		if (!used[sl]) continue;
-		/* +-1 incidence entries are literals: reciprocals of such pivots, and the
-		 * multipliers built from them, fold at compile time (1/1 and x*1 are
-		 * exact, so the results do not change), and the stamp needs no register */
-		if (sl < p.nnzA && active[sl] && cst[sl] == cst[sl])
-			o.f("\tdouble w%d = %s;\n", sl, lit(cst[sl]).c_str());
-		else if (sl < p.nnzA && active[sl]) o.f("\tdouble w%d = c.Av[%d];\n", sl, sl);
-		else o.f("\tdouble w%d = 0.0;\n", sl);
-	}
-	for (int r = 0; r < N; r++) o.f("\tdouble y%d = c.Bv[%d];\n", r, r);
-	int pos = 0;
-	std::vector<int> start(N);
+	if (blocks <= 0) for (int v = 0; v < F + N; v++) uf[v] = 0;     /* one block */
+	/* blocks in the order of their first pivot step; which ones a linearize pass reaches */
+	std::vector<int> blockOf(F + N, -1), roots;
 	for (int k = 0; k < N; k++) {
-		start[k] = pos;
-		const int d = s.lu[pos], yk = s.lu[pos + 1] - F, nU = s.lu[pos + 2], nL = s.lu[pos + 3];
-		const int *u = &s.lu[pos + 4];
-		const int *lrow = u + 2 * nU;
-		o.f("\tconst double i%d = 1.0 / w%d; bad |= (w%d == 0.0) | !isfinite(i%d);\n", k, d, d, k);
-		for (int r = 0; r < nL; r++) {
-			const int *e = lrow + r * (2 + nU);
-			/* growth guard: the fixed sequence was chosen on pilot instances; a
-			 * multiplier this large means the pivot has lost that many digits */
-			o.f("\t{ const double l = w%d * i%d;%s", e[0], k, guard ? " grow |= (fabs(l) > SIMCU_LMAX);" : "");
-			for (int j = 0; j < nU; j++) o.f(" w%d -= l * w%d;", e[2 + j], u[2 * j]);
-			o.f(" y%d -= l * y%d; }\n", e[1] - F, yk);
+		const int r = find(s.lu[start[k]]);
+		if (blockOf[r] < 0) { blockOf[r] = (int)roots.size(); roots.push_back(r); }
+	}
+	for (int v = 0; v < F + N; v++) blockOf[v] = blockOf[find(v)];
+	const int nb = (int)roots.size();
+	std::vector<char> touched(nb, 1);
+	if (blocks >= 2) {
+		std::vector<char> tslot, trow;
+		newtonTouched(p, tslot, trow);
+		o.f("/* linearize can change A slots:");
+		for (int sl = 0; sl < p.nnzA; sl++) if (tslot[sl]) o.f(" %d", sl);
+		o.f("; B rows:");
+		for (int r = 1; r <= N; r++) if (trow[r]) o.f(" %d", r);
+		o.f(" */\n");
+		touched.assign(nb, 0);
+		for (int sl = 0; sl < p.nnzA; sl++) if (tslot[sl] && used[sl] && blockOf[sl] >= 0) touched[blockOf[sl]] = 1;
+		for (int r = 1; r <= N; r++) if (trow[r] && blockOf[F + r - 1] >= 0) touched[blockOf[F + r - 1]] = 1;
+	}
+	int nInvariant = 0;
+	for (int b = 0; b < nb; b++) nInvariant += !touched[b];
+	o.f("/* %d independent block%s, %d of them not reached by any linearize stamp */\n", nb, nb == 1 ? "" : "s",
+			(blocks >= 2) ? nInvariant : 0);
+	o.f("DEV void genFactorSolve%d(Inst &c, const bool first)\n{\n\tbool bad = false, grow = false;\n\t(void)first;\n",
+			phase);
+	auto emitBlock = [&](int b, const char *growVar) {
+		o.f("\t{\n");
+		for (int sl = 0; sl < F; sl++) {
+			if (!used[sl] || blockOf[sl] != b) continue;
+			/* +-1 incidence entries are literals: reciprocals of such pivots, and the
+			 * multipliers built from them, fold at compile time (1/1 and x*1 are
+			 * exact, so the results do not change), and the stamp needs no register */
+			if (sl < p.nnzA && active[sl] && cst[sl] == cst[sl])
+				o.f("\tdouble w%d = %s;\n", sl, lit(cst[sl]).c_str());
+			else if (sl < p.nnzA && active[sl]) o.f("\tdouble w%d = c.Av[%d];\n", sl, sl);
+			else o.f("\tdouble w%d = 0.0;\n", sl);
 		}
-		pos += 4 + 2 * nU + nL * (2 + nU);
+		for (int r = 0; r < N; r++) if (blockOf[F + r] == b) o.f("\tdouble y%d = c.Bv[%d];\n", r, r);
+		for (int k = 0; k < N; k++) {
+			const int pos = start[k];
+			const int d = s.lu[pos], yk = s.lu[pos + 1] - F, nU = s.lu[pos + 2], nL = s.lu[pos + 3];
+			if (blockOf[d] != b) continue;
+			const int *u = &s.lu[pos + 4];
+			const int *lrow = u + 2 * nU;
+			o.f("\tconst double i%d = 1.0 / w%d; bad |= (w%d == 0.0) | !isfinite(i%d);\n", k, d, d, k);
+			for (int r = 0; r < nL; r++) {
+				const int *e = lrow + r * (2 + nU);
+				/* growth guard: the fixed sequence was chosen on pilot instances; a
+				 * multiplier this large means the pivot has lost that many digits */
+				o.f("\t{ const double l = w%d * i%d;", e[0], k);
+				if (guard) o.f(" %s |= (fabs(l) > SIMCU_LMAX);", growVar);
+				for (int j = 0; j < nU; j++) o.f(" w%d -= l * w%d;", e[2 + j], u[2 * j]);
+				o.f(" y%d -= l * y%d; }\n", e[1] - F, yk);
+			}
+		}
+		/* back substitution, reverse pivot order; the solution of column pc[k]
+		 * replaces the right-hand side of its pivot row */
+		for (int k = N - 1; k >= 0; k--) {
+			const int q = start[k];
+			if (blockOf[s.lu[q]] != b) continue;
+			const int yk = s.lu[q + 1] - F, nU = s.lu[q + 2];
+			const int *u = &s.lu[q + 4];
+			o.f("\t{ double acc = y%d;", yk);
+			for (int j = 0; j < nU; j++) o.f(" acc -= w%d * y%d;", u[2 * j], u[2 * j + 1] - F);
+			o.f(" y%d = acc * i%d; }\n", yk, k);
+		}
+		for (int col = 0; col < N; col++)
+			if (blockOf[s.xslot[col]] == b) o.f("\tc.Xv[%d] = y%d;\n", col, s.xslot[col] - F);
+		o.f("\t}\n");
+	};
+	if (blocks >= 2 && nInvariant > 0) {
+		/* growth seen in these blocks counts for every solve of the loop, as if they
+		 * had been factorised again */
+		o.f("\tif (first) {\n\tbool growInv = false;\n");
+		for (int b = 0; b < nb; b++) if (!touched[b]) emitBlock(b, "growInv");
+		o.f("\tc.growInv = growInv;\n\t}\n\tgrow |= c.growInv;\n");
 	}
-	/* back substitution, reverse pivot order; the solution of column pc[k]
-	 * replaces the right-hand side of its pivot row */
-	for (int k = N - 1; k >= 0; k--) {
-		const int q = start[k];
-		const int yk = s.lu[q + 1] - F, nU = s.lu[q + 2];
-		const int *u = &s.lu[q + 4];
-		o.f("\t{ double acc = y%d;", yk);
-		for (int j = 0; j < nU; j++) o.f(" acc -= w%d * y%d;", u[2 * j], u[2 * j + 1] - F);
-		o.f(" y%d = acc * i%d; }\n", yk, k);
-	}
-	for (int col = 0; col < N; col++) o.f("\tc.Xv[%d] = y%d;\n", col, s.xslot[col] - F);
+	for (int b = 0; b < nb; b++) if (touched[b] || blocks < 2) emitBlock(b, "grow");
 	o.f("\tif (bad) c.err = SIMCU_ERR_SINGULAR;\n\tif (grow) c.growth++;\n}\n\n");
 }
 
@@ -624,6 +732,7 @@ std::string generatePrelude(const Program &p, int numProbes, int numMeasures, co
 	o.f("#define SIMCU_BLOCKSYNC %d\n#define SIMCU_SYNCGROUP %d\n", cfg.blockSync ? 1 : 0, cfg.syncGroup);
 	o.f("#define SIMCU_WINDOWS %d\n#define SIMCU_SMEMTAB %d\n", cfg.windows ? 1 : 0, cfg.smemTab ? 1 : 0);
 	o.f("#define SIMCU_FMAD %d   /* compiled with --fmad=%s */\n", cfg.fmad ? 1 : 0, cfg.fmad ? "true" : "false");
+	o.f("#define SIMCU_SHAREDCB %d\n", cfg.sharedCb ? 1 : 0);
 	o.f("#define HUGE_VAL (__longlong_as_double(0x7ff0000000000000LL))\n");
 	o.f("#define SIMCU_GMIN (%s)\n", lit(gmin).c_str());
 	o.f("#define SIMCU_LMAX (%s)\n", lit(cfg.growthLimit).c_str());
@@ -637,15 +746,15 @@ std::string generatePrelude(const Program &p, int numProbes, int numMeasures, co
 
 std::string generateTopology(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
-		const std::vector<int> &probeRows, const std::vector<int> &measures, bool growthGuard,
-		bool tlinePrefetch)
+		const std::vector<int> &probeRows, const std::vector<int> &measures, const JitConfig &cfg)
 {
 	Out o;
+	const bool growthGuard = cfg.growthLimit > 0.0;
 	o.f("/* ---- generated for this netlist by simcu_codegen.cpp ---- */\n");
 	emitCalcAll(o, p);
-	emitPhases(o, p, tlinePrefetch);
-	emitFactorSolve(o, p, sched[0], active[0], consts[0], 0, growthGuard);
-	emitFactorSolve(o, p, sched[1], active[1], consts[1], 1, growthGuard);
+	emitPhases(o, p, cfg.tlinePrefetch != 0, cfg.sharedCb != 0);
+	emitFactorSolve(o, p, sched[0], active[0], consts[0], 0, growthGuard, cfg.solveBlocks);
+	emitFactorSolve(o, p, sched[1], active[1], consts[1], 1, growthGuard, cfg.solveBlocks);
 	emitSaveRecall(o, p, probeRows, measures);
 	emitRows(o, "genHistRows", p.histRows);
 	emitRows(o, "genProbeRows", probeRows);

@@ -25,11 +25,15 @@ struct JitConfig {
 	double growthLimit = 1e6; /* LU multipliers above this are counted (pivot growth guard; <= 0: off) */
 	int tlinePrefetch = 0;    /* circuits with >= 2 T-lines: locate + prefetch pass before the step */
 	int fmad = 0;             /* 0: no a*b+c contraction: the reference's (and the oracle's) arithmetic */
+	int solveBlocks = 2;      /* LU + solves emitted block by block (1), blocks no linearize stamp reaches
+	                           * only in the first solve of a Newton loop (2); 0: all at once */
+	int sharedCb = 1;         /* one break-point clock per instance instead of one per device */
 	bool operator==(const JitConfig &o) const
 	{
 		return threadsPerBlock == o.threadsPerBlock && minBlocks == o.minBlocks && gmin == o.gmin &&
 			replay == o.replay && blockSync == o.blockSync && syncGroup == o.syncGroup && windows == o.windows && smemTab == o.smemTab && growthLimit == o.growthLimit &&
-			tlinePrefetch == o.tlinePrefetch && fmad == o.fmad;
+			tlinePrefetch == o.tlinePrefetch && fmad == o.fmad && solveBlocks == o.solveBlocks &&
+			sharedCb == o.sharedCb;
 	}
 };
 
@@ -38,8 +42,7 @@ std::string generatePrelude(const Program &p, int numProbes, int numMeasures, co
 /* device records, expressions and the unrolled LU of both phases */
 std::string generateTopology(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],
-		const std::vector<int> &probeRows, const std::vector<int> &measures, bool growthGuard,
-		bool tlinePrefetch);
+		const std::vector<int> &probeRows, const std::vector<int> &measures, const JitConfig &cfg);
 /* prelude + embedded library headers + topology + kernel */
 std::string assembleSource(const Program &p, const Schedule sched[2],
 		const std::vector<char> active[2], const std::vector<double> consts[2],

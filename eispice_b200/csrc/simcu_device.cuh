@@ -108,6 +108,12 @@ struct Inst {
 	mutable double itT[4], itH[3];
 	mutable int itN;
 	mutable bool itAdv;
+	/* ... and of the break-point tests that run at every attempt (checkbreak.c:43-67:
+	 * t[] and the dt of theta[p] are the same in all of them) */
+	mutable double cbT0, cbT1, cbDt1;
+	mutable int cbN;
+	mutable bool cbAdv;
+	bool growInv;        /* pivot growth seen in the Newton-invariant blocks of this attempt */
 	double par[SIMCU_DIM(SIMCU_NPARAM)];
 	int tset[SIMCU_DIM(SIMCU_NISET)];
 
@@ -355,7 +361,41 @@ DEV int cbIsBreak(const Inst &c, int sb, int ib, double x, double maxAngle)
 	const double dy = x - c.S(sb + 1), dt = c.time - c.S(sb + 4);
 	return cbAngleBreak(dy, dt, c.S(sb + 7), c.S(sb + 5), maxAngle);
 }
+
+#ifndef SIMCU_SHAREDCB
+#define SIMCU_SHAREDCB 0
+#endif
+#if SIMCU_SHAREDCB
+/* Every break-point test that runs at EVERY attempt - sources, TA tables, time
+ * dependent B sources, the first test of a T-line - is initialised at load and
+ * called at the same times, so their t0 / t1 / dt1 / n hold identical values:
+ * one copy per instance, advanced once per step phase (cbBegin), and three
+ * doubles of state (x0, x1, dx1) per test instead of six.  Same operands, same
+ * tests.  Only a T-line's second test (skipped whenever the first one breaks,
+ * tline.c:196-203) keeps its own clock. */
+DEV void cbBegin(const Inst &c)
+{
+	c.cbAdv = (c.time > c.cbT0);
+	if (c.cbAdv) { c.cbN++; c.cbDt1 = c.cbT0 - c.cbT1; c.cbT1 = c.cbT0; }
+	c.cbT0 = c.time;
+}
+
+DEV int cbIsBreakClocked(const Inst &c, int sb, int ib, double x, double maxAngle)
+{
+	(void)ib;
+	if (c.cbAdv) {
+		c.S(sb + 7) = c.S(sb) - c.S(sb + 1);
+		c.S(sb + 1) = c.S(sb);
+	}
+	c.S(sb) = x;
+	if (c.cbN < 1) return 0;
+	return cbAngleBreak(x - c.S(sb + 1), c.time - c.cbT1, c.S(sb + 7), c.cbDt1, maxAngle);
+}
 #else
+#define cbIsBreakClocked cbIsBreak
+#endif
+#else
+#define cbIsBreakClocked cbIsBreak
 DEV void cbInitialize(const Inst &c, int sb, int ib, double ic)
 {
 	for (int k = 0; k < 3; k++) { c.D(sb + k) = ic; c.D(sb + 3 + k) = 0.0; }
@@ -1128,7 +1168,7 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 		if (type == DK_V) c.Bplus(d[DF_ROWR], dc - old);
 		else { c.Bplus(d[DF_K], -(dc - old)); c.Bplus(d[DF_J], dc - old); }
 		c.S(sb) = dc;
-		return cbIsBreak(c, sb + 1, ib, dc, (type == DK_V) ? k.maxAngleV : k.maxAngleA);
+		return cbIsBreakClocked(c, sb + 1, ib, dc, (type == DK_V) ? k.maxAngleV : k.maxAngleA);
 	}
 	case DK_VI: {                               /* vicurve.c:85-106 */
 		if (d[DF_TATAB] < 0) return 0;
@@ -1139,7 +1179,7 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 		pwCalcValue(ta, idx, c.time, aa, dadt);
 		c.IS(ib + 3) = idx;
 		c.S(sb + 2) = aa;
-		return cbIsBreak(c, sb + 4, ib + 1, aa, k.maxAngleA);
+		return cbIsBreakClocked(c, sb + 4, ib + 1, aa, k.maxAngleA);
 	}
 	case DK_T: {                                /* tline.c:126-204 */
 		if (d[DF_PBYPASS] >= 0 && c.P(d[DF_PBYPASS]) != 0.0) return 0;
@@ -1179,7 +1219,7 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 		}
 		c.Bplus(d[DF_ROWR], Vr - c.S(sb)); c.S(sb) = Vr;
 		c.Bplus(d[DF_ROWS], Vs - c.S(sb + 1)); c.S(sb + 1) = Vs;
-		int brk = cbIsBreak(c, sb + 6, ib, Vr, k.maxAngleV);
+		int brk = cbIsBreakClocked(c, sb + 6, ib, Vr, k.maxAngleV);
 		if (!brk) brk = cbIsBreak(c, sb + 15, ib + 1, Vs, k.maxAngleV);
 		return brk;
 	}
@@ -1187,7 +1227,7 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 		if (!d[DF_USETIME]) return 0;
 		bCalculate(c, d, true);
 		if (!c.err) bLoad(c, d, bv);
-		return cbIsBreak(c, sb + 4, ib + 1, c.S(sb + 2),
+		return cbIsBreakClocked(c, sb + 4, ib + 1, c.S(sb + 2),
 				(type == DK_BV) ? k.maxAngleV : k.maxAngleA);
 	case DK_BC:                                 /* nonlinear_c.c:172-184 */
 		if (!d[DF_USETIME]) return 0;

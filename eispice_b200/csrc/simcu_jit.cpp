@@ -101,8 +101,7 @@ std::string assembleSource(const Program &p, const Schedule sched[2],
 	s += kSrcProgram;
 	s += kSrcCalc;
 	s += kSrcDevice;
-	s += generateTopology(p, sched, active, consts, probeRows, measures, cfg.growthLimit > 0.0,
-			cfg.tlinePrefetch != 0);
+	s += generateTopology(p, sched, active, consts, probeRows, measures, cfg);
 	s += kSrcJitKernel;
 	return s;
 }

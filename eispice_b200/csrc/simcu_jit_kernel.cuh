@@ -173,6 +173,8 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 				SIMCU_UNROLL
 				for (int s = 0; s < SIMCU_SI; s++) c.iv[s] = 0;
 				c.itN = 0; c.itAdv = false;
+				c.cbT0 = 0.0; c.cbT1 = 0.0; c.cbDt1 = 0.0; c.cbN = 0; c.cbAdv = false;
+				c.growInv = false;
 				SIMCU_UNROLL
 				for (int j = 0; j < 4; j++) c.itT[j] = 0.0;
 				SIMCU_UNROLL
@@ -232,8 +234,10 @@ extern "C" __global__ void __launch_bounds__(SIMCU_TPB, SIMCU_MINB) simcuJitKern
 		int count = 0;
 		if (!done) {
 			for (;;) {
-				if (transient) { genFactorSolve1(c); nfact++; }
-				else { genFactorSolve0(c); nfactOp++; }
+				/* count == 0: the first solve of this loop; later ones skip the blocks
+				 * no linearize stamp reaches (same stamps, same solution) */
+				if (transient) { genFactorSolve1(c, count == 0); nfact++; }
+				else { genFactorSolve0(c, count == 0); nfactOp++; }
 				/* pivot breakdown in a transient attempt (the fixed sequence met a
 				 * zero / non-finite pivot, or one that lost all its digits): reject
 				 * the attempt as non-convergent, so the step is cut and Newton

@@ -171,6 +171,12 @@ int simcuSetInstanceWindow(simcu_ *r, const double *tstep, const double *tstop, 
  * sequence it then reproduces the reference algorithm bit for bit wherever no
  * libm function is involved; 1 allows contraction: 0-3 % faster, results differ
  * in the last bits and step sequences may differ),
+ * solve_blocks (generated LU of the specialised kernel: 0 = all at once, 1 =
+ * regrouped by independent matrix block - T-lines decouple their ports - so only
+ * one block is live at a time, 2 = default: additionally the blocks no linearize
+ * stamp reaches are solved only in the first solve of a Newton loop; results
+ * are bit-identical in all three), shared_break_clock (default 1: one
+ * break-point clock per instance instead of one per device, same decisions),
  * replay (see simcuSetReplayLog);
  * r = NULL: quiet (0/1) */
 int simcuSetOption(simcu_ *r, char *name, double value);

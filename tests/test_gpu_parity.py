@@ -618,3 +618,28 @@ def test_adaptive_run_is_bit_identical_to_the_oracle_under_the_same_pivots(cfg, 
         identical += int(raws[i].shape == od.shape and np.array_equal(raws[i], od))
     assert identical == w.M, "%d of %d instances bit-identical" % (identical, w.M)
     eng.close()
+
+
+@pytest.mark.parametrize("cfg,M", [("cfg5", 768), ("cfg4", 1024), ("cfg2", 256), ("cfg5_masked", 256)])
+def test_block_ordered_solve_and_shared_break_clock_do_not_change_a_bit(cfg, M):
+    """The generated LU emitted block by block, with the blocks no linearize stamp
+    reaches solved once per Newton loop (solve_blocks = 2), and the one
+    break-point clock per instance (shared_break_clock = 1) - the defaults - are
+    reorganisations of the same operations: waveforms, statuses and every counter
+    equal those of the plain emission with per-device clocks, bit for bit."""
+    w = workloads.cfg5_masked(M) if cfg == "cfg5_masked" else workloads.make(cfg, M)
+    runs = []
+    for opts in ({"solve_blocks": 0, "shared_break_clock": 0}, {"solve_blocks": 1, "shared_break_clock": 0},
+                 {}):
+        eng = engine.Engine(w.cct.netlist(), w.M)
+        res = eng.tran_batch(w.tstep, w.tstop, 0.0, w.params, w.probes, threads_per_block=128,
+                             block_sync=1, **opts)
+        runs.append((res.data.copy(), res.status.copy(),
+                     {k: res.stats[k] for k in ("accepted", "factorizations", "rejectedLTE", "rejectedNC",
+                                                "failed", "growthWarnings")}))
+        eng.close()
+    assert runs[0][2]["accepted"] > 100 * M / 4
+    for data, status, stats in runs[1:]:
+        assert np.array_equal(runs[0][0], data, equal_nan=True)
+        assert np.array_equal(runs[0][1], status)
+        assert stats == runs[0][2]

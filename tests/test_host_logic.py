@@ -311,12 +311,14 @@ def test_specialised_source_is_independent_of_instances_and_values():
 
 # ---- generated LU: compile the emitted straight-line code for the HOST and
 # ---- check it against a dense solve ------------------------------------------
-def _host_lu_harness(src, tmp_path, phase):
-    """Builds a shared object around genFactorSolve<phase> of a generated source."""
+def _host_lu_harness(src, tmp_path, phase, tag=""):
+    """Builds a shared object around genFactorSolve<phase> of a generated source.
+    solve(A, B, X, first): X is in/out, so a later solve of a Newton loop
+    (first = 0) can leave the blocks no linearize stamp reaches as they are."""
     import ctypes as C
     import subprocess
     name = "genFactorSolve%d" % phase
-    body = src[src.index("DEV void %s(Inst &c)" % name):]
+    body = src[src.index("DEV void %s(Inst &c, const bool first)" % name):]
     body = body[:body.index("\n}\n") + 3]
     n = int(re.search(r"#define SIMCU_N (\d+)", src).group(1))
     nnz = int(re.search(r"#define SIMCU_NNZ (\d+)", src).group(1))
@@ -328,19 +330,20 @@ def _host_lu_harness(src, tmp_path, phase):
 #define SIMCU_LMAX 1e6
 using std::isfinite;
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
-struct Inst { double Av[%d], Bv[%d], Xv[%d]; int err, growth; };
+struct Inst { double Av[%d], Bv[%d], Xv[%d]; int err, growth; bool growInv; };
 %s
-extern "C" int solve(const double *A, const double *B, double *X)
+extern "C" int solve(const double *A, const double *B, double *X, int first)
 {
-	Inst c; c.err = 0; c.growth = 0;
+	Inst c; c.err = 0; c.growth = 0; c.growInv = false;
 	std::memcpy(c.Av, A, sizeof c.Av); std::memcpy(c.Bv, B, sizeof c.Bv);
-	%s(c);
+	std::memcpy(c.Xv, X, sizeof c.Xv);
+	%s(c, first != 0);
 	std::memcpy(X, c.Xv, sizeof c.Xv);
 	return c.err;
 }
 """ % (max(nnz, 1), n, n, body, name)
-    cpp = tmp_path / ("lu%d.cpp" % phase)
-    so = tmp_path / ("lu%d.so" % phase)
+    cpp = tmp_path / ("lu%d%s.cpp" % (phase, tag))
+    so = tmp_path / ("lu%d%s.so" % (phase, tag))
     cpp.write_text(code)
     subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cpp)],
                    check=True)
@@ -381,11 +384,67 @@ def test_generated_lu_solves_the_system(name, tmp_path):
         b = rng.normal(size=n)
         x = np.zeros(n)
         err = lib.solve(A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
-                        x.ctypes.data_as(C.c_void_p))
+                        x.ctypes.data_as(C.c_void_p), 1)
         assert err == 0
         want = np.linalg.solve(dense, b)
         assert np.allclose(x, want, rtol=1e-8, atol=1e-9 * np.abs(want).max()), (name, phase)
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["cfg5", "cfg4", "cfg2", "cfg5_masked"])
+def test_block_ordered_lu_is_bit_identical_and_later_solves_skip_only_invariant_blocks(name, tmp_path):
+    """The generated LU regrouped block by block (solve_blocks = 1) and with the
+    blocks no linearize stamp reaches run only in the first solve of a Newton
+    loop (2, the default) gives, bit for bit, the solution of the all-at-once
+    emission (0) - also in a LATER solve, after everything a linearize pass can
+    change (the slots and rows the generated code lists) has changed."""
+    import ctypes as C
+    import workloads
+    w = workloads.cfg5_masked(16) if name == "cfg5_masked" else workloads.make(name, 16)
+    srcs = {}
+    for blocks in (0, 1, 2):
+        eng = engine.Engine(w.cct.netlist(), w.M)
+        eng.set_option("solve_blocks", blocks)
+        eng.set_params(w.params)
+        srcs[blocks] = eng.compile_only(w.probes)[0]
+        eng.close()
+    rng = np.random.default_rng(11)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    for phase in (0, 1):
+        libs = {b: _host_lu_harness(srcs[b], tmp_path, phase, "b%d" % b) for b in (0, 1, 2)}
+        _, n, nnz, _, loaded = libs[0]
+        body = srcs[2][srcs[2].index("/* %s:" % ("transient" if phase else "operating point")):]
+        m = re.search(r"/\* linearize can change A slots:([ \d]*); B rows:([ \d]*) \*/", body)
+        tslots = [int(v) for v in m.group(1).split()]
+        trows = [int(v) for v in m.group(2).split()]
+        ninv = int(re.search(r"(\d+) of them not reached by any linearize stamp", body).group(1))
+        if name == "cfg5" and phase == 1:
+            assert ninv >= 7            # the inner nodes of the 8-section line
+        if name == "cfg2":
+            assert ninv == 0 or len(tslots) > 0
+        for trial in range(20):
+            A = np.zeros(max(nnz, 1))
+            for sl in loaded:
+                A[sl] = rng.uniform(0.5, 2.0) * rng.choice([-1.0, 1.0])
+            b = rng.normal(size=n)
+            xs = {}
+            for blk, (lib, *_rest) in libs.items():
+                x = np.full(n, np.nan)
+                lib.solve(ptr(A), ptr(b), ptr(x), 1)
+                xs[blk] = x
+            assert xs[0].tobytes() == xs[1].tobytes() == xs[2].tobytes(), (name, phase, trial)
+            # a later solve of the same loop: only what linearize can change changed
+            A2, b2 = A.copy(), b.copy()
+            for sl in tslots:
+                if sl in loaded:
+                    A2[sl] = rng.uniform(0.5, 2.0) * rng.choice([-1.0, 1.0])
+            for r in trows:
+                b2[r - 1] = rng.normal()
+            full = np.full(n, np.nan)
+            libs[0][0].solve(ptr(A2), ptr(b2), ptr(full), 1)
+            later = xs[2].copy()
+            libs[2][0].solve(ptr(A2), ptr(b2), ptr(later), 0)
+            assert full.tobytes() == later.tobytes(), (name, phase, trial)
 
 
 # ---- generated expression code: compile genCalc / genCalcGrad for the HOST and
@@ -555,3 +614,86 @@ def test_cubin_cache_on_disk(tmp_path, monkeypatch):
     files = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
     assert len(files) == 1 and sizes[0] == sizes[1] == os.path.getsize(os.path.join(tmp_path, files[0]))
     assert t[1] < 0.5 * t[0], t
+
+
+# ---- shared break-point clock: compile the device functions for the HOST and
+# ---- compare them with the per-device clocks on random attempt sequences ------
+def test_shared_break_clock_equals_the_per_device_clocks(tmp_path):
+    """checkbreak.c:43-67 keeps t[] per device; every test that runs at every
+    attempt sees the same times, so the specialised kernel keeps ONE clock per
+    instance (cbBegin / cbIsBreakClocked).  Same decisions, same state, on random
+    sequences of attempts incl. rejected ones (time steps back) and flat signals."""
+    import ctypes as C
+    import subprocess
+    dev = open(os.path.join(ROOT, "eispice_b200", "csrc", "simcu_device.cuh")).read()
+    start = dev.index("DEVFN int cbAngleBreak(")
+    end = dev.index("#else\n#define cbIsBreakClocked cbIsBreak\nDEV void cbInitialize")
+    code = """
+#include <cmath>
+#define DEV static inline
+#define DEVFN static
+#define SIMCU_JIT 1
+#define SIMCU_SHAREDCB 1
+#define HUGE_VAL (__builtin_huge_val())
+static double simcuAtan2(double y, double x) { return atan2(y, x); }
+struct Inst {
+	mutable double sv[32]; mutable int iv[4]; double time;
+	mutable double cbT0, cbT1, cbDt1; mutable int cbN; mutable bool cbAdv;
+	double &S(int i) const { return sv[i]; }
+	int &IS(int i) const { return iv[i]; }
+};
+%s
+extern "C" int run(int n, const double *t, const double *x, double maxAngle, int *own, int *clocked, double *state)
+{
+	Inst c;
+	cbInitialize(c, 0, 0, 0.0); cbInitialize(c, 9, 1, 0.0);
+	c.cbT0 = 0.0; c.cbT1 = 0.0; c.cbDt1 = 0.0; c.cbN = 0; c.cbAdv = false;
+	for (int k = 0; k < n; k++) {
+		c.time = t[k];
+		cbBegin(c);
+		own[k] = cbIsBreak(c, 0, 0, x[k], maxAngle);
+		clocked[k] = cbIsBreakClocked(c, 9, 1, x[k], maxAngle);
+		if (c.S(0) != c.S(9) || c.S(1) != c.S(10) || c.S(7) != c.S(16)) return k + 1;
+		if (c.S(3) != c.cbT0 || c.S(4) != c.cbT1 || c.S(5) != c.cbDt1 || c.IS(0) != c.cbN) return -(k + 1);
+	}
+	(void)state;
+	return 0;
+}
+""" % dev[start:end]
+    cpp, so = tmp_path / "cb.cpp", tmp_path / "cb.so"
+    cpp.write_text(code)
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cpp)],
+                   check=True)
+    lib = C.CDLL(str(so))
+    lib.run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    breaks = 0
+    for trial in range(200):
+        n = 400
+        t = np.zeros(n)
+        now, last_ok = 0.0, 0.0
+        for k in range(n):
+            u = rng.random()
+            if u < 0.2 and k:            # rejected attempt: retry from the last accepted time
+                now = last_ok + (now - last_ok) * rng.choice([0.125, 0.5, 0.9])
+            else:
+                last_ok = now
+                now = now + 1e-11 * 10 ** rng.uniform(-3, 1)
+            t[k] = now
+        kind = trial % 4
+        if kind == 0:
+            x = np.cumsum(rng.normal(size=n)) * 1e-3
+        elif kind == 1:
+            x = np.where(rng.random(n) < 0.7, 1.25, rng.normal(size=n))      # mostly flat
+        elif kind == 2:
+            x = 1e-12 * np.cumsum(rng.normal(size=n))                       # angles near the threshold
+        else:
+            x = np.sin(2e9 * t) * 3.3
+        own = np.zeros(n, dtype=np.int32)
+        clk = np.zeros(n, dtype=np.int32)
+        rc = lib.run(n, t.ctypes.data, x.ctypes.data, 1.0471975511965976, own.ctypes.data,
+                     clk.ctypes.data, None)
+        assert rc == 0, (trial, rc)
+        assert (own == clk).all(), trial
+        breaks += int(own.sum())
+    assert breaks > 100
