@@ -447,7 +447,8 @@ def main():
                        "local_bytes_per_thread": st["localBytesPerThread"],
                        "l2": "flushed between timed steps (256 MiB write)",
                        "failed_instances": int(failed_all), "status_rank0": status_hist,
-                       "prepare_s": round(prepare_s, 3), "nvrtc": engine.nvrtc_path(),
+                       "prepare_s": round(prepare_s, 3),
+                       "nvrtc_s": round(st["jitCompileMs"] * 1e-3, 3), "nvrtc": engine.nvrtc_path(),
                        "e2e_steps": e2e_steps,
                        "e2e_host_buffers": "pinned" if pinned else "pageable"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -894,7 +895,9 @@ int buildJitKernel(simcu_ *r)
 	else {
 		std::shared_ptr<JitKernel> k(new JitKernel());
 		std::string err;
+		const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
 		if (!jitCompile(src, *k, err, cfg.fmad != 0)) return fail("%s", err.c_str());
+		r->stats.jitCompileMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 		if (!jitLoad(*k, r->tpb, err)) return fail("%s", err.c_str());
 		/* bounded: drop entries no handle uses any more, oldest key first */
 		for (it = gKernelCache.begin(); it != gKernelCache.end() && gKernelCache.size() >= kKernelCacheMax;) {

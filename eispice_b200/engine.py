@@ -42,7 +42,7 @@ class Stats(C.Structure):
                 ("localBytesPerThread", C.c_int), ("gridBlocks", C.c_int),
                 ("lanesPerWarp", C.c_int), ("pivotBreakdowns", C.c_longlong),
                 ("historyRetries", C.c_int), ("replayDiffs", C.c_longlong),
-                ("growthWarnings", C.c_longlong)]
+                ("growthWarnings", C.c_longlong), ("jitCompileMs", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

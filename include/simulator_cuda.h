@@ -73,6 +73,7 @@ typedef struct {
 	long long growthWarnings;  /* factorisations whose largest LU multiplier exceeded growth_limit:
 	                            * the fixed pivot sequence (chosen on pilot instances) lost that many
 	                            * digits on this instance; per instance: counter "pivot_growth" */
+	double jitCompileMs;       /* wall time this handle spent compiling (NVRTC, or reading the cubin cache) */
 } simcuStats_;
 
 /* simulatorNew (simulator.h:33): r must be NULL */
