@@ -1005,6 +1005,11 @@ struct eo_sim {
 	/* per linearize pass (simulatorSolve :57-58), operating point included: bit k =
 	 * the tolerance tests of the k-th nonlinear device passed (checklinear.c:62-77) */
 	int linN, linCap; int *linMask;
+	/* stamp watch (tests only): which A entries / B rows differed between two
+	 * consecutive solves of ONE simulatorSolve loop, per phase */
+	int watchOn;
+	double *watchA, *watchB;        /* stamps at the previous solve of this loop */
+	char *changedA[2], *changedB[2];
 };
 
 /* --- rows & pattern: core/row.c:46-66,163-204, core/matrix.c:292-346 ------ */
@@ -1123,6 +1128,8 @@ void eoDestroy(eo_sim *s)
 	free(s->htime); free(s->hX);
 	for (i = 0; i < 2; i++) { free(s->fixPc[i]); free(s->fixPr[i]); }
 	free(s->logTime); free(s->logFlag); free(s->linMask);
+	free(s->watchA); free(s->watchB);
+	for (i = 0; i < 2; i++) { free(s->changedA[i]); free(s->changedB[i]); }
 	free(s);
 }
 void eoFree(void *p) { free(p); }
@@ -1834,10 +1841,34 @@ int eoSetPivots(eo_sim *s, int phase, const int *pc, const int *pr, int n)
 }
 
 /* simulatorSolve: core/simulator.c:45-69.  Returns the reference's count. */
+/* stamp watch: first = 1 remembers the stamps of the loop's first solve, later
+ * calls mark what changed since the previous solve (test instrumentation: the
+ * engine solves the matrix blocks nothing here can reach only once per loop) */
+static void watchStamps(eo_sim *s, int first)
+{
+	int N = s->N, i;
+	if (!s->watchOn) return;
+	if (s->watchA == NULL) {
+		s->watchA = malloc(sizeof(double) * N * N + 8); s->watchB = malloc(sizeof(double) * N + 8);
+		for (i = 0; i < 2; i++) {
+			s->changedA[i] = calloc((size_t)N * N + 1, 1); s->changedB[i] = calloc(N + 1, 1);
+		}
+	}
+	if (!first) {
+		for (i = 0; i < N * N; i++)
+			if (memcmp(&s->A[i], &s->watchA[i], sizeof(double))) s->changedA[s->phase][i] = 1;
+		for (i = 0; i < N; i++)
+			if (memcmp(&s->B[i], &s->watchB[i], sizeof(double))) s->changedB[s->phase][i] = 1;
+	}
+	memcpy(s->watchA, s->A, sizeof(double) * N * N);
+	memcpy(s->watchB, s->B, sizeof(double) * N);
+}
+
 static int simSolve(eo_sim *s, int limit)
 {
 	int count = 0, linear, i;
 	if (limit < 1) return -1;
+	watchStamps(s, 1);
 	TRY(luSolve(s));
 	while (count++ < limit) {
 		int mask = 0, bit = 0;
@@ -1861,6 +1892,7 @@ static int simSolve(eo_sim *s, int limit)
 			s->linMask[s->linN++] = mask;
 		}
 		if (linear) break;
+		watchStamps(s, 0);
 		TRY(luSolve(s));
 	}
 	return count;
@@ -2002,6 +2034,16 @@ static void logAttempt(eo_sim *s, double time, int order, int outcome, int solve
 }
 
 void eoSetAttemptLog(eo_sim *s, int on) { s->logOn = on; s->logN = 0; s->linN = 0; }
+
+void eoSetStampWatch(eo_sim *s, int on) { s->watchOn = on; }
+
+int eoGetStampWatch(eo_sim *s, int phase, const char **a, const char **b)
+{
+	if (phase < 0 || phase > 1 || s->changedA[0] == NULL) return 0;
+	if (a) *a = s->changedA[phase];
+	if (b) *b = s->changedB[phase];
+	return s->N;
+}
 
 int eoGetLinearizeLog(eo_sim *s, const int **masks)
 {

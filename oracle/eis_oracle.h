@@ -80,6 +80,15 @@ int eoGetAttemptLog(eo_sim *s, const double **times, const int **flags);
  * reltol that a 1-ulp difference can flip.  At most 31 nonlinear devices. */
 int eoGetLinearizeLog(eo_sim *s, const int **masks);
 
+/* Stamp watch (test instrumentation): with on = 1 the runs record which A
+ * entries (dense, a[row * N + col], 0-based unknowns) and which right-hand-side
+ * rows differed between two consecutive solves of ONE simulatorSolve loop
+ * (core/simulator.c:45-69), per phase (0 operating point, 1 transient).
+ * Returns N (0: nothing recorded yet).  The engine's claim "only linearize
+ * stamps change inside a Newton loop" is checked against this. */
+void eoSetStampWatch(eo_sim *s, int on);
+int eoGetStampWatch(eo_sim *s, int phase, const char **a, const char **b);
+
 int eoRunTransient(eo_sim *s, double tstep, double tstop, double tmax,
 		int restart, double **data, char ***variables, int *numPoints,
 		int *numVariables);

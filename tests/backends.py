@@ -76,6 +76,8 @@ def oracle_lib():
         lib.eoSetAttemptLog.argtypes = [C.c_void_p, C.c_int]
         lib.eoGetAttemptLog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.eoGetLinearizeLog.argtypes = [C.c_void_p, C.c_void_p]
+        lib.eoSetStampWatch.argtypes = [C.c_void_p, C.c_int]
+        lib.eoGetStampWatch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _oracle = lib
     return _oracle
 
@@ -230,6 +232,20 @@ class OracleSim:
         if n == 0:
             return np.zeros(0, dtype=np.int32)
         return np.ctypeslib.as_array(m, shape=(n,)).copy()
+
+    def watch_stamps(self, on=True):
+        self.lib.eoSetStampWatch(self.h, 1 if on else 0)
+
+    def stamp_changes(self, phase):
+        """(A[N, N] bool, B[N] bool): what differed between two consecutive solves
+        of one Newton loop in the runs since watch_stamps() (None: nothing ran)."""
+        a, b = C.POINTER(C.c_char)(), C.POINTER(C.c_char)()
+        n = self.lib.eoGetStampWatch(self.h, phase, C.byref(a), C.byref(b))
+        if n == 0:
+            return None
+        A = np.frombuffer(C.string_at(a, n * n), dtype=np.uint8).reshape(n, n).astype(bool)
+        B = np.frombuffer(C.string_at(b, n), dtype=np.uint8).astype(bool)
+        return A, B
 
     def stats(self):
         st = EoStats()

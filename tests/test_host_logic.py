@@ -15,7 +15,7 @@ import pytest
 
 import backends
 import circuits
-from eispice_b200 import engine
+from eispice_b200 import engine, units
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -697,3 +697,70 @@ extern "C" int run(int n, const double *t, const double *x, double maxAngle, int
         assert (own == clk).all(), trial
         breaks += int(own.sum())
     assert breaks > 100
+
+
+# ---- "only linearize stamps change inside a Newton loop": the claim behind
+# ---- solve_blocks = 2, checked against the oracle's stamps on every circuit ----
+def _declared_newton_stamps(src, phase):
+    body = src[src.index("/* %s:" % ("transient" if phase else "operating point")):]
+    m = re.search(r"/\* linearize can change A slots:([ \d]*); B rows:([ \d]*) \*/", body)
+    return [int(v) for v in m.group(1).split()], [int(v) for v in m.group(2).split()]
+
+
+def _check_newton_stamps(nl, vi_set, an, label):
+    eng = engine.Engine(nl, 1)
+    src, _ = eng.compile_only(eng.variables()[1:2])
+    n, ri, cs = eng.pattern()
+    col = np.repeat(np.arange(n), np.diff(cs))
+    eng.close()
+    ora = backends.OracleSim(nl, vi_set)
+    ora.watch_stamps()
+    if an[0] == "op":
+        ora.op()
+    else:
+        try:
+            ora.tran(*[units.float(x) for x in an[1:]])
+        except RuntimeError:
+            pass                      # an aborted run still watched every loop it made
+    seen = 0
+    for phase in (0, 1):
+        got = ora.stamp_changes(phase)
+        if got is None:
+            continue
+        A, B = got
+        slots, rows = _declared_newton_stamps(src, phase)
+        allowed = np.zeros((n, n), dtype=bool)
+        for s in slots:
+            allowed[ri[s], col[s]] = True
+        rows_ok = np.zeros(n, dtype=bool)
+        for r in rows:
+            rows_ok[r - 1] = True
+        assert not (A & ~allowed).any(), (label, phase, np.argwhere(A & ~allowed)[:5].tolist())
+        assert not (B & ~rows_ok).any(), (label, phase, np.flatnonzero(B & ~rows_ok)[:5].tolist())
+        seen += int(A.sum()) + int(B.sum())
+    return seen
+
+
+def test_only_the_declared_stamps_change_inside_a_newton_loop():
+    """solve_blocks = 2 solves a matrix block only in the first solve of a
+    simulatorSolve loop (core/simulator.c:45-69) if no A slot / right-hand-side
+    row the generated code lists as "linearize can change" lies in it.  The
+    oracle - pinned to the reference - watches its own stamps between consecutive
+    solves of every loop of every golden circuit and of the IBIS links: whatever
+    changed must be on that list."""
+    import workloads
+    total = 0
+    nonlinear = 0
+    for name, (build, an, _checks) in sorted(circuits.all_cases().items()):
+        seen = _check_newton_stamps(build().netlist(), 0, an, name)
+        total += 1
+        nonlinear += seen > 0
+    for cfg, picks in (("cfg4", (0, 5)), ("cfg5", (3,)), ("cfg2", (7,)), ("cfg3", (1,))):
+        w = workloads.make(cfg, 16)
+        for i in picks:
+            nl, vi_set = w.instance_netlist(i)
+            seen = _check_newton_stamps(nl, vi_set, ("tran", w.tstep, w.tstop), "%s[%d]" % (cfg, i))
+            assert seen > 0
+            total += 1
+            nonlinear += 1
+    assert total >= 30 and nonlinear >= 10
