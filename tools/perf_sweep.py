@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Device-resident timing of one workload under several engine options.
 usage: perf_sweep.py cfg M "opt=val,opt=val" ["..." ...]   (empty string = defaults)
-Appends one JSON line per variant to gpurun_out/perf_sweep.jsonl."""
+Appends one JSON line per variant to gpurun_out/perf_sweep.jsonl.
+Note: an explicit threads_per_block switches the automatic launch-shape policy
+off, block_sync included - pass block_sync=1 with it to compare block sizes."""
 import json
 import os
 import sys
