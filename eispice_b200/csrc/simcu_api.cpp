@@ -1661,10 +1661,11 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	cfg.solveBlocks = r->solveBlocks; cfg.sharedCb = r->sharedCb;
 	const std::string src = assembleSource(p, sched, active, consts, probeRows, r->measures, cfg);
 	if (source) *source = strdup(src.c_str());
+	if (!cubinBytes) return 0;          /* the generated source only */
 	JitKernel k;
 	std::string err;
 	if (!jitCompile(src, k, err, cfg.fmad != 0)) return fail("%s", err.c_str());
-	if (cubinBytes) *cubinBytes = (int)k.cubin.size();
+	*cubinBytes = (int)k.cubin.size();
 	return 0;
 }
 

@@ -579,13 +579,13 @@ class Engine:
         res.measures = meas
         return res
 
-    def compile_only(self, probes=()):
+    def compile_only(self, probes=(), source_only=False):
         """(source text, cubin bytes) of the topology-specialised kernel; needs
-        NVRTC but no GPU."""
+        NVRTC but no GPU.  source_only: generate the source, skip NVRTC (0 bytes)."""
         src = C.c_void_p()
         n = C.c_int()
         rc = self.L.simcuCompileOnly(self.h, self._probe_array(probes), len(probes),
-                                     C.byref(src), C.byref(n))
+                                     C.byref(src), None if source_only else C.byref(n))
         text = C.string_at(src).decode() if src.value else ""
         if src.value:
             self.L.simcuFree(src)

@@ -342,7 +342,8 @@ const char *simcuVariableName(simcu_ *r, int k);
 int simcuGetPivots(simcu_ *r, int phase, int *pc, int *pr);
 /* test hook (no GPU needed): flatten, structural symbolic analysis, source
  * generation and NVRTC compilation of the topology-specialised kernel.
- * *source (optional) receives the malloc'd translation unit. */
+ * *source (optional) receives the malloc'd translation unit; cubinBytes = NULL
+ * stops after the source generation (no NVRTC). */
 int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source,
 		int *cubinBytes);
 /* test hook: the symbolic analysis alone.  CSC pattern + numPilots value sets
