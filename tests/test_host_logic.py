@@ -774,3 +774,86 @@ def test_only_the_declared_stamps_change_inside_a_newton_loop():
             total += 1
             nonlinear += 1
     assert total >= 30 and nonlinear >= 10
+
+
+# ---- T-line history search: compile tlineLocateFn for the HOST and compare it with
+# ---- the reference's record-by-record walk on random rings ---------------------
+def _walk_like_the_reference(times, lo, count, hint, tp):
+    """math/history_interp.c:42-64 + core/history.c:36-59 restated: walk from the
+    hint record to THE record with t_j <= tp < t_(j+1) (or the newest one with
+    t_j <= tp); past the newest record the last two are used (extrapolation).
+    Returns (landing record, earlier, later) in record numbers, or None when the
+    records needed have left the ring."""
+    i = hint if lo <= hint < count else lo
+    while i > lo and times[i] > tp:
+        i -= 1
+    if times[i] > tp:
+        return None
+    while i + 1 < count and times[i + 1] <= tp:
+        i += 1
+    if i + 1 < count:
+        return i, i, i + 1
+    if i - 1 < lo:
+        return None
+    return i, i - 1, i
+
+
+def test_tline_history_search_lands_where_the_reference_walk_lands(tmp_path):
+    """The galloping + binary search of the kernel (tlineLocateFn) returns the ring
+    positions of the same two records as the reference's walk, for any hint, with
+    wrapped rings, delayed times before the oldest and past the newest record."""
+    import ctypes as C
+    import subprocess
+    dev = open(os.path.join(ROOT, "eispice_b200", "csrc", "simcu_device.cuh")).read()
+    start = dev.index("DEV int tlineWrap(int p, int R)")
+    end = dev.index("DEV double tlineInterp(")
+    code = """
+#define DEV static inline
+#define DEVFN static
+struct int4 { int x, y, z, w; };
+%s
+extern "C" void locate(const double *times, int R, int count, int hint, double tp, int *out)
+{
+	const int4 r = tlineLocateFn(times, R, count, hint, tp);
+	out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+""" % dev[start:end]
+    cpp, so = tmp_path / "loc.cpp", tmp_path / "loc.so"
+    cpp.write_text(code)
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", str(so), str(cpp)], check=True)
+    lib = C.CDLL(str(so))
+    lib.locate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    rng = np.random.default_rng(9)
+    found = gone = 0
+    for trial in range(300):
+        R = int(rng.choice([4, 7, 16, 33, 64]))
+        count = int(rng.integers(1, 4 * R))
+        # strictly increasing accepted times with bursts of tiny steps
+        steps = 10 ** rng.uniform(-15, -10, count)
+        t = np.concatenate(([0.0], np.cumsum(steps)))[:count]
+        ring = np.full(R, np.nan)
+        lo = max(0, count - R)
+        for q in range(lo, count):
+            ring[q % R] = t[q]
+        for _ in range(40):
+            hint = int(rng.integers(-2, count + 3))
+            u = rng.random()
+            if u < 0.1:
+                tp = float(t[int(rng.integers(lo, count))])            # exactly on a record
+            elif u < 0.2:
+                tp = float(t[count - 1] + 10 ** rng.uniform(-14, -10))   # past the newest
+            else:
+                tp = float(rng.uniform(0.0 if lo == 0 else t[lo] * 0.9, t[count - 1] * 1.05))
+            want = _walk_like_the_reference(t, lo, count, hint, tp)
+            out = (C.c_int * 4)()
+            lib.locate(ring.ctypes.data, R, count, hint, tp, out)
+            if want is None:
+                assert out[3] == 0, (trial, R, count, hint, tp, list(out))
+                gone += 1
+            else:
+                land, a, b = want
+                assert out[3] != 0 and out[0] == land, (trial, R, count, hint, tp, list(out), want)
+                assert (out[1], out[2]) == (a % R, b % R)
+                assert out[3] - 1 == land % R
+                found += 1
+    assert found > 5000 and gone > 50
