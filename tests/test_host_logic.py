@@ -857,3 +857,73 @@ extern "C" void locate(const double *times, int R, int count, int hint, double t
                 assert out[3] - 1 == land % R
                 found += 1
     assert found > 5000 and gone > 50
+
+
+def test_break_angle_shortcut_decides_like_the_two_atan2(tmp_path):
+    """checkbreak.c:57-66 compares two atan2 angles in raw SI units; the kernel's
+    cbAngleBreak settles most calls from certified bounds on the arguments and
+    from single-precision angles, and falls back to the reference's expression
+    otherwise.  Host build, 23 million argument pairs incl. zeros,
+    infinities, NaNs, negative and equal time differences: same decision."""
+    import ctypes as C
+    import subprocess
+    dev = open(os.path.join(ROOT, "eispice_b200", "csrc", "simcu_device.cuh")).read()
+    start = dev.index("DEVFN int cbAngleBreak(")
+    end = dev.index("/* state (6 live doubles of the 9 slots)")
+    code = """
+#include <cmath>
+#define DEV static inline
+#define DEVFN static
+#define HUGE_VAL (__builtin_huge_val())
+static double simcuAtan2(double y, double x) { return (y == 0.0 && x > 0.0) ? y : atan2(y, x); }
+%s
+extern "C" long check(long n, const double *dy0, const double *dx0, const double *dy1, const double *dx1,
+		double maxAngle, long *breaks)
+{
+	long bad = 0, nb = 0;
+	for (long k = 0; k < n; k++) {
+		const int want = (fabs(simcuAtan2(dy0[k], dx0[k]) - simcuAtan2(dy1[k], dx1[k])) > maxAngle) ? 1 : 0;
+		const int got = cbAngleBreak(dy0[k], dx0[k], dy1[k], dx1[k], maxAngle);
+		bad += (want != got);
+		nb += want;
+	}
+	*breaks = nb;
+	return bad;
+}
+""" % dev[start:end]
+    cpp, so = tmp_path / "ang.cpp", tmp_path / "ang.so"
+    cpp.write_text(code)
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(cpp)], check=True)
+    lib = C.CDLL(str(so))
+    lib.check.restype = C.c_long
+    lib.check.argtypes = [C.c_long] + [C.c_void_p] * 4 + [C.c_double, C.c_void_p]
+    rng = np.random.default_rng(21)
+    n = 1 << 19
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 1e-300, 1e300, 1e-11, 1.0])
+
+    def sample(kind):
+        mag = 10.0 ** rng.uniform(-22, 3, n)
+        dy = mag * rng.choice([-1.0, 1.0], n)
+        dy[rng.random(n) < 0.25] = 0.0
+        dx = 10.0 ** rng.uniform(-16, -8, n)
+        if kind == 1:                       # near the threshold: |dy| ~ dx
+            dy = dx * rng.uniform(-4, 4, n)
+        if kind == 2:                       # special values sprinkled in
+            hit = rng.random(n) < 0.3
+            dy[hit] = rng.choice(special, hit.sum())
+            hit = rng.random(n) < 0.3
+            dx[hit] = rng.choice(np.concatenate((special, -special[6:])), hit.sum())
+        return np.ascontiguousarray(dy), np.ascontiguousarray(dx)
+
+    total_breaks = 0
+    for angle in (math.pi / 3, 0.95, 1.09, 0.5, 1.3):
+        for k0 in range(3):
+            for k1 in range(3):
+                dy0, dx0 = sample(k0)
+                dy1, dx1 = sample(k1)
+                nb = C.c_long()
+                bad = lib.check(n, dy0.ctypes.data, dx0.ctypes.data, dy1.ctypes.data, dx1.ctypes.data,
+                                angle, C.byref(nb))
+                assert bad == 0, (angle, k0, k1, bad)
+                total_breaks += nb.value
+    assert total_breaks > 1 << 19
