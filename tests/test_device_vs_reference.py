@@ -1,0 +1,268 @@
+"""Device code against the UNMODIFIED reference, function by function, on the CPU.
+
+The numerical-integration and break-point modules of the kernel are
+re-organised relative to libs/simulator/math (rings stored by age, one shared
+time ring, the negative-ring-index quirk spelled out, the angle test decided
+from its arguments).  These tests compile exactly those device functions of
+eispice_b200/csrc/simcu_device.cuh for the HOST (g++, no contraction) and drive
+them side by side with the reference's own integrator.c / checkbreak.c from
+oracle/_ref/libeispice_ref.so (built from the reference's sources by
+oracle/build_ref.sh) through the call pattern of core/simulator.c:142-233 -
+attempts that advance, attempts that step back after a reject, order changes.
+Every output must be bit-identical.
+
+Test infrastructure only: a host build of device functions is not a CPU path
+of the product (the engine has none).  Skipped where oracle/_ref is absent.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import backends
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEVICE = os.path.join(ROOT, "eispice_b200", "csrc", "simcu_device.cuh")
+PROGRAM = os.path.join(ROOT, "eispice_b200", "csrc", "simcu_program.h")
+
+pytestmark = pytest.mark.skipif(not backends.ref_available(), reason="needs oracle/_ref (the reference build)")
+
+
+class Control(C.Structure):
+    """control_ of libs/simulator/include/control.h:35-56"""
+    _fields_ = [("itl1", C.c_int), ("itl4", C.c_int), ("reltol", C.c_double), ("vntol", C.c_double),
+                ("captol", C.c_double), ("abstol", C.c_double), ("chgtol", C.c_double),
+                ("trtol", C.c_double), ("minstep", C.c_double), ("gmin", C.c_double),
+                ("maxorder", C.c_int), ("luLibrary", C.c_int), ("maxAngleA", C.c_double),
+                ("maxAngleV", C.c_double), ("tstop", C.c_double), ("tstep", C.c_double),
+                ("integratorOrder", C.c_int), ("time", C.c_double)]
+
+
+def _control(tstop=15e-9, tstep=1e-11):
+    c = Control()
+    c.itl1, c.itl4, c.maxorder = 100, 10, 2
+    c.reltol, c.vntol, c.abstol, c.captol = 1e-3, 1e-6, 1e-12, 1e-18
+    c.chgtol, c.trtol, c.gmin = 1e-14, 1.0, 1e-15
+    c.minstep = tstep * 5e-5
+    c.maxAngleA = c.maxAngleV = np.pi / 3
+    c.tstop, c.tstep = tstop, tstep
+    c.integratorOrder, c.time = 1, 0.0
+    return c
+
+
+def _host_device_lib(tmp_path):
+    dev = open(DEVICE).read()
+    prog = open(PROGRAM).read()
+    integ = dev[dev.index("DEV double DD1("):dev.index("#else\n#define RING(c, sb, k, j)")] + "#endif\n"
+    brk = dev[dev.index("DEVFN int cbAngleBreak("):
+              dev.index("#else\n#define cbIsBreakClocked cbIsBreak\nDEV void cbInitialize")]
+    code = """
+#include <cmath>
+#include <cstring>
+using std::isnan;
+%s
+#define DEV static inline
+#define DEVFN static
+#define SIMCU_JIT 1
+#define SIMCU_SHAREDCB 1
+#define SIMCU_UNROLL
+#define HUGE_VAL (__builtin_huge_val())
+#define MaxAbs(x, y) ((fabs(x) > fabs(y)) ? fabs(x) : fabs(y))
+#define MUL_RN(a, b) ((a) * (b))
+#define ADD_RN(a, b) ((a) + (b))
+#define W_TSTOP(c) ((c).a.ctl.tstop)
+enum { SIMCU_ERR_NAN = 3 };
+static double simcuAtan2(double y, double x) { return (y == 0.0 && x > 0.0) ? y : atan2(y, x); }
+struct Inst {
+	SimcuArgs a;
+	double time; int order; int err;
+	mutable double sv[64]; mutable int iv[8];
+	mutable double itT[4], itH[3]; mutable int itN; mutable bool itAdv;
+	mutable double cbT0, cbT1, cbDt1; mutable int cbN; mutable bool cbAdv;
+	double &S(int i) const { return sv[i]; }
+	int &IS(int i) const { return iv[i]; }
+};
+%s
+%s
+extern "C" {
+void *devNew(double tstop, double reltol, double chgtol, double trtol, double gmin)
+{
+	Inst *c = new Inst();
+	std::memset(c, 0, sizeof *c);
+	c->a.ctl.tstop = tstop; c->a.ctl.reltol = reltol; c->a.ctl.chgtol = chgtol;
+	c->a.ctl.trtol = trtol; c->a.ctl.gmin = gmin;
+	return c;
+}
+void devFree(void *h) { delete (Inst *)h; }
+void devItInit(void *h, double ic, double ydtdx) { itInitialize(*(Inst *)h, 0, 0, ic, ydtdx); }
+int devItIntegrate(void *h, double time, int order, double x0, double ydtdx, double *dydx0, double *y0)
+{
+	Inst &c = *(Inst *)h;
+	c.time = time; c.order = order; c.err = 0;
+	itBegin(c);
+	itIntegrate(c, 0, 0, x0, ydtdx, *dydx0, *y0);
+	return c.err;
+}
+int devItNextStep(void *h, double x0, double ydtdx, double abstol, double *step)
+{
+	Inst &c = *(Inst *)h;
+	c.err = 0;
+	*step = itNextStep(c, 0, 0, x0, ydtdx, abstol);
+	return c.err;
+}
+void devCbInit(void *h, double ic)
+{
+	Inst &c = *(Inst *)h;
+	cbInitialize(c, 30, 0, ic); cbInitialize(c, 40, 1, ic);
+	c.cbT0 = 0.0; c.cbT1 = 0.0; c.cbDt1 = 0.0; c.cbN = 0; c.cbAdv = false;      /* as at the claim */
+}
+/* the per-device clock (a T-line's second test) and the instance's shared clock */
+int devCbIsBreak(void *h, double time, double x, double maxAngle, int *clocked)
+{
+	Inst &c = *(Inst *)h;
+	c.time = time;
+	cbBegin(c);
+	*clocked = cbIsBreakClocked(c, 40, 1, x, maxAngle);
+	return cbIsBreak(c, 30, 0, x, maxAngle);
+}
+}
+""" % (prog, integ, brk)
+    cpp, so = tmp_path / "dev.cpp", tmp_path / "dev.so"
+    cpp.write_text(code)
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-o", str(so), str(cpp)],
+                   check=True)
+    lib = C.CDLL(str(so))
+    lib.devNew.restype = C.c_void_p
+    lib.devNew.argtypes = [C.c_double] * 5
+    lib.devFree.argtypes = [C.c_void_p]
+    lib.devItInit.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.devItIntegrate.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    lib.devItNextStep.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.devCbInit.argtypes = [C.c_void_p, C.c_double]
+    lib.devCbIsBreak.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    return lib
+
+
+def _reference():
+    ref = backends.ref_lib()
+    ref.integratorNew.restype = C.c_void_p
+    ref.integratorNew.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char]
+    ref.integratorInitialize.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+    ref.integratorIntegrate.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    ref.integratorNextStep.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+    ref.checkbreakNew.restype = C.c_void_p
+    ref.checkbreakNew.argtypes = [C.c_void_p, C.c_void_p, C.c_char]
+    ref.checkbreakInitialize.argtypes = [C.c_void_p, C.c_double]
+    ref.checkbreakIsBreak.argtypes = [C.c_void_p, C.c_double]
+    return ref
+
+
+def _bits(x):
+    return np.float64(x).tobytes()
+
+
+def _attempt_times(rng, n, tstep):
+    """Attempt times as core/simulator.c:156-218 produces them: forward after an
+    accept, a shorter step from the last accepted time after a reject."""
+    t, accepted = [], []
+    last_ok, now = 0.0, 0.0
+    step = tstep / 100
+    for _ in range(n):
+        now = last_ok + step
+        ok = rng.random() > 0.25
+        t.append(now)
+        accepted.append(ok)
+        if ok:
+            last_ok = now
+            step = step * rng.choice([0.1, 1.0, 2.0])
+        else:
+            step = step * rng.choice([0.125, 0.5, 0.9])
+    return t, accepted
+
+
+@pytest.mark.parametrize("units,ydtdx_kind", [("V", "const"), ("A", "const"), ("F", "varying")])
+def test_integrator_equals_the_references_integrator(tmp_path, units, ydtdx_kind):
+    """math/integrator.c:61-163 incl. the negative ring index while the counter is
+    below the look-back (:90-96) and the float sqrtf (:99): companion model (G,
+    Ieq) and LTE step of the device code, bit for bit, on random runs."""
+    dev, ref = _host_device_lib(tmp_path), _reference()
+    rng = np.random.default_rng({"V": 1, "A": 2, "F": 3}[units])
+    compared = 0
+    for trial in range(60):
+        ctl = _control()
+        ydtdx = C.c_double(10.0 ** rng.uniform(-13, -8))
+        abstol = {"V": ctl.vntol, "A": ctl.abstol, "F": ctl.captol}[units]
+        h = dev.devNew(ctl.tstop, ctl.reltol, ctl.chgtol, ctl.trtol, ctl.gmin)
+        r = ref.integratorNew(None, C.byref(ctl), C.byref(ydtdx), units.encode())
+        assert r
+        ic = float(rng.normal())
+        # devLoad initialises with 0, devInitStep with the operating point
+        dev.devItInit(h, 0.0, ydtdx.value)
+        assert ref.integratorInitialize(r, ic, C.byref(ydtdx)) == 0
+        dev.devItInit(h, ic, ydtdx.value)
+        times, accepted = _attempt_times(rng, 120, ctl.tstep)
+        x_ok = ic
+        order = 2                                        # core/simulator.c:133
+        for tm, ok in zip(times, accepted):
+            if ydtdx_kind == "varying":
+                ydtdx.value = ydtdx.value * float(rng.uniform(0.9, 1.1))
+            ctl.time, ctl.integratorOrder = tm, order
+            d0, y0 = C.c_double(), C.c_double()
+            assert ref.integratorIntegrate(r, x_ok, C.byref(d0), C.byref(y0)) == 0
+            d1, y1 = C.c_double(), C.c_double()
+            assert dev.devItIntegrate(h, tm, order, x_ok, ydtdx.value, C.byref(d1), C.byref(y1)) == 0
+            assert _bits(d0.value) == _bits(d1.value) and _bits(y0.value) == _bits(y1.value), (trial, tm, order)
+            x_new = x_ok + float(rng.normal()) * 10.0 ** rng.uniform(-6, -1) * (rng.random() > 0.2)
+            s0, s1 = C.c_double(), C.c_double()
+            rc0 = ref.integratorNextStep(r, x_new, C.byref(s0))
+            rc1 = dev.devItNextStep(h, x_new, ydtdx.value, abstol, C.byref(s1))
+            assert (rc0 != 0) == (rc1 != 0)
+            if rc0 == 0:
+                assert _bits(s0.value) == _bits(s1.value), (trial, tm, order, s0.value, s1.value)
+                compared += 1
+            if ok:
+                x_ok = x_new
+                order = min(order + 1, 2)
+            else:
+                order = 1 if rng.random() < 0.5 else max(order - 1, 1)
+        dev.devFree(h)
+    assert compared > 5000
+
+
+def test_break_point_test_equals_the_references_checkbreak(tmp_path):
+    """math/checkbreak.c:43-67 against the device code - the per-device version (state
+    by age, arguments instead of angles) and the one with the instance's shared
+    clock (cbBegin / cbIsBreakClocked): same decision at every call."""
+    dev, ref = _host_device_lib(tmp_path), _reference()
+    rng = np.random.default_rng(17)
+    calls = breaks = 0
+    for trial in range(80):
+        ctl = _control()
+        h = dev.devNew(ctl.tstop, ctl.reltol, ctl.chgtol, ctl.trtol, ctl.gmin)
+        r = ref.checkbreakNew(None, C.byref(ctl), b"V")
+        assert r
+        assert ref.checkbreakInitialize(r, 0.0) == 0
+        dev.devCbInit(h, 0.0)
+        times, _ = _attempt_times(rng, 200, ctl.tstep)
+        kind = trial % 4
+        x = 0.0
+        for k, tm in enumerate(times):
+            if kind == 0:
+                x += float(rng.normal()) * 1e-2
+            elif kind == 1:
+                x = 1.8 if (k // 25) % 2 else 0.0                      # pulse plateaus and edges
+            elif kind == 2:
+                x += float(rng.normal()) * 1e-12 * (rng.random() > 0.5)   # angles near the threshold
+            else:
+                x = 3.3 * np.sin(2e9 * tm)
+            ctl.time = tm
+            want = ref.checkbreakIsBreak(r, x)
+            clocked = C.c_int()
+            got = dev.devCbIsBreak(h, tm, x, ctl.maxAngleV, C.byref(clocked))
+            assert want == got == clocked.value, (trial, k, tm, x)
+            calls += 1
+            breaks += got
+        dev.devFree(h)
+    assert calls == 16000 and breaks > 200
