@@ -56,6 +56,7 @@ def _host_device_lib(tmp_path):
     dev = open(DEVICE).read()
     prog = open(PROGRAM).read()
     integ = dev[dev.index("DEV double DD1("):dev.index("#else\n#define RING(c, sb, k, j)")] + "#endif\n"
+    conv = dev[dev.index("DEV int clIsLinear("):dev.index("/* ------------------------------------------------------------------------ *\n * Integrator:")]
     brk = dev[dev.index("DEVFN int cbAngleBreak("):
               dev.index("#else\n#define cbIsBreakClocked cbIsBreak\nDEV void cbInitialize")]
     code = """
@@ -84,6 +85,7 @@ struct Inst {
 	double &S(int i) const { return sv[i]; }
 	int &IS(int i) const { return iv[i]; }
 };
+%s
 %s
 %s
 extern "C" {
@@ -127,8 +129,10 @@ int devCbIsBreak(void *h, double time, double x, double maxAngle, int *clocked)
 	*clocked = cbIsBreakClocked(c, 40, 1, x, maxAngle);
 	return cbIsBreak(c, 30, 0, x, maxAngle);
 }
+void devClInit(void *h, double ic) { Inst &c = *(Inst *)h; c.S(50) = ic; c.IS(4) = 0; }
+int devClIsLinear(void *h, double tol, double V, double calcedV) { return clIsLinear(*(Inst *)h, 50, 4, tol, V, calcedV); }
 }
-""" % (prog, integ, brk)
+""" % (prog, integ, brk, conv)
     cpp, so = tmp_path / "dev.cpp", tmp_path / "dev.so"
     cpp.write_text(code)
     subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-o", str(so), str(cpp)],
@@ -142,6 +146,8 @@ int devCbIsBreak(void *h, double time, double x, double maxAngle, int *clocked)
     lib.devItNextStep.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.devCbInit.argtypes = [C.c_void_p, C.c_double]
     lib.devCbIsBreak.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.devClInit.argtypes = [C.c_void_p, C.c_double]
+    lib.devClIsLinear.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
     return lib
 
 
@@ -156,6 +162,10 @@ def _reference():
     ref.checkbreakNew.argtypes = [C.c_void_p, C.c_void_p, C.c_char]
     ref.checkbreakInitialize.argtypes = [C.c_void_p, C.c_double]
     ref.checkbreakIsBreak.argtypes = [C.c_void_p, C.c_double]
+    ref.checklinearNew.restype = C.c_void_p
+    ref.checklinearNew.argtypes = [C.c_void_p, C.c_void_p, C.c_char]
+    ref.checklinearInitialize.argtypes = [C.c_void_p, C.c_double]
+    ref.checklinearIsLinear.argtypes = [C.c_void_p, C.c_double, C.c_double]
     return ref
 
 
@@ -266,3 +276,36 @@ def test_break_point_test_equals_the_references_checkbreak(tmp_path):
             breaks += got
         dev.devFree(h)
     assert calls == 16000 and breaks > 200
+
+
+@pytest.mark.parametrize("units", ["V", "A", "F"])
+def test_convergence_test_equals_the_references_checklinear(tmp_path, units):
+    """math/checklinear.c:39-91: two tolerance tests at reltol and the a -> b -> c
+    state that survives across timesteps - the decision that ends a Newton loop."""
+    dev, ref = _host_device_lib(tmp_path), _reference()
+    rng = np.random.default_rng(ord(units))
+    ctl = _control()
+    tol = {"V": ctl.vntol, "A": ctl.abstol, "F": ctl.captol}[units]
+    scale = {"V": 1.0, "A": 1e-2, "F": 1e-12}[units]
+    passes = calls = 0
+    for trial in range(200):
+        h = dev.devNew(ctl.tstop, ctl.reltol, ctl.chgtol, ctl.trtol, ctl.gmin)
+        r = ref.checklinearNew(None, C.byref(ctl), units.encode())
+        ic = float(rng.normal()) * scale
+        assert ref.checklinearInitialize(r, ic) == 0
+        dev.devClInit(h, ic)
+        v = ic
+        for k in range(60):
+            u = rng.random()
+            if u < 0.5:                      # converging: changes around the tolerance
+                v = v * (1 + float(rng.normal()) * 10.0 ** rng.uniform(-6, -2))
+            elif u < 0.6:
+                v = float(rng.normal()) * scale
+            calced = v * (1 + float(rng.normal()) * 10.0 ** rng.uniform(-6, -2)) + float(rng.normal()) * tol
+            want = ref.checklinearIsLinear(r, v, calced)
+            got = dev.devClIsLinear(h, tol, v, calced)
+            assert want == got, (trial, k, v, calced)
+            passes += got
+            calls += 1
+        dev.devFree(h)
+    assert calls == 12000 and 500 < passes < calls - 500
