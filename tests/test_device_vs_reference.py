@@ -56,6 +56,7 @@ def _host_device_lib(tmp_path):
     dev = open(DEVICE).read()
     prog = open(PROGRAM).read()
     integ = dev[dev.index("DEV double DD1("):dev.index("#else\n#define RING(c, sb, k, j)")] + "#endif\n"
+    wave = dev[dev.index("DEV double wfArg("):dev.index("/* ------------------------------------------------------------------------ *\n * Behavioural sources:")]
     conv = dev[dev.index("DEV int clIsLinear("):dev.index("/* ------------------------------------------------------------------------ *\n * Integrator:")]
     brk = dev[dev.index("DEVFN int cbAngleBreak("):
               dev.index("#else\n#define cbIsBreakClocked cbIsBreak\nDEV void cbInitialize")]
@@ -82,11 +83,21 @@ struct Inst {
 	mutable double sv[64]; mutable int iv[8];
 	mutable double itT[4], itH[3]; mutable int itN; mutable bool itAdv;
 	mutable double cbT0, cbT1, cbDt1; mutable int cbN; mutable bool cbAdv;
+	double par[8];
+	double P(int i) const { return par[i]; }
+	int tableSet(int) const { return 0; }
 	double &S(int i) const { return sv[i]; }
 	int &IS(int i) const { return iv[i]; }
 };
 %s
 %s
+%s
+/* table waveforms ('l' / 'c') are not exercised here: stubs for the code to compile */
+#define W_TSTEP(c) ((c).a.ctl.tstep)
+struct Table { const double *p; int len; int type; };
+static Table tableOf(const SimcuArgs &, int) { Table t = {0, 0, 0}; return t; }
+static void pwCalcValue(const Table &, int &, double, double &y, double &d) { y = 0; d = 0; }
+static double pwGetNextX(const Table &, int &, double) { return HUGE_VAL; }
 %s
 extern "C" {
 void *devNew(double tstop, double reltol, double chgtol, double trtol, double gmin)
@@ -129,10 +140,22 @@ int devCbIsBreak(void *h, double time, double x, double maxAngle, int *clocked)
 	*clocked = cbIsBreakClocked(c, 40, 1, x, maxAngle);
 	return cbIsBreak(c, 30, 0, x, maxAngle);
 }
+void devWave(void *h, int type, const double *args, double time, double tstep, double tstop,
+		double *value, double *next)
+{
+	Inst &c = *(Inst *)h;
+	int d[SIMCU_DEV_STRIDE] = {0};
+	d[DF_WTYPE] = type; d[DF_PARGS] = 0;
+	for (int k = 0; k < 7; k++) c.par[k] = args[k];
+	c.a.ctl.tstep = tstep; c.a.ctl.tstop = tstop;
+	c.time = time;
+	*value = wfValue(c, d, 0, 0);
+	wfNextStep(c, d, 0, *next);
+}
 void devClInit(void *h, double ic) { Inst &c = *(Inst *)h; c.S(50) = ic; c.IS(4) = 0; }
 int devClIsLinear(void *h, double tol, double V, double calcedV) { return clIsLinear(*(Inst *)h, 50, 4, tol, V, calcedV); }
 }
-""" % (prog, integ, brk, conv)
+""" % (prog, integ, brk, conv, wave)
     cpp, so = tmp_path / "dev.cpp", tmp_path / "dev.so"
     cpp.write_text(code)
     subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-o", str(so), str(cpp)],
@@ -146,6 +169,7 @@ int devClIsLinear(void *h, double tol, double V, double calcedV) { return clIsLi
     lib.devItNextStep.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.devCbInit.argtypes = [C.c_void_p, C.c_double]
     lib.devCbIsBreak.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.devWave.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_double] * 3 + [C.c_void_p, C.c_void_p]
     lib.devClInit.argtypes = [C.c_void_p, C.c_double]
     lib.devClIsLinear.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
     return lib
@@ -162,6 +186,11 @@ def _reference():
     ref.checkbreakNew.argtypes = [C.c_void_p, C.c_void_p, C.c_char]
     ref.checkbreakInitialize.argtypes = [C.c_void_p, C.c_double]
     ref.checkbreakIsBreak.argtypes = [C.c_void_p, C.c_double]
+    ref.waveformNew.restype = C.c_void_p
+    ref.waveformNew.argtypes = [C.c_void_p, C.c_void_p, C.c_char, C.c_void_p, C.c_void_p]
+    ref.waveformInitialize.argtypes = [C.c_void_p]
+    ref.waveformCalcValue.argtypes = [C.c_void_p, C.c_void_p]
+    ref.waveformNextStep.argtypes = [C.c_void_p, C.c_void_p]
     ref.checklinearNew.restype = C.c_void_p
     ref.checklinearNew.argtypes = [C.c_void_p, C.c_void_p, C.c_char]
     ref.checklinearInitialize.argtypes = [C.c_void_p, C.c_double]
@@ -309,3 +338,57 @@ def test_convergence_test_equals_the_references_checklinear(tmp_path, units):
             calls += 1
         dev.devFree(h)
     assert calls == 12000 and 500 < passes < calls - 500
+
+
+@pytest.mark.parametrize("kind", ["p", "g", "s", "e", "f"])
+def test_source_waveforms_equal_the_references_waveform(tmp_path, kind):
+    """math/waveform.c:169-413: Pulse, Gauss, Sin, Exp and SFFM - value and the
+    look-ahead to the next corner - with every combination of omitted arguments
+    (HUGE_VAL), whose defaults depend on tstep / tstop of the run (:342-413)."""
+    dev, ref = _host_device_lib(tmp_path), _reference()
+    rng = np.random.default_rng(ord(kind))
+    nargs = {"p": 7, "g": 7, "s": 5, "e": 6, "f": 5}[kind]
+    optional = {"p": (2, 4, 5, 6), "g": (2, 4, 5, 6), "s": (2, 3, 4), "e": (2, 3, 4, 5), "f": (2, 3, 4)}[kind]
+    compared = 0
+    for trial in range(150):
+        tstep = 10.0 ** rng.uniform(-12, -9)
+        tstop = tstep * float(rng.integers(50, 2000))
+        ctl = _control(tstop, tstep)
+        a = np.full(7, np.inf)
+        a[0], a[1] = rng.normal(), rng.normal() * 3
+        span = tstop
+        if kind in "pg":
+            a[2:7] = [rng.uniform(0, 0.2) * span, rng.uniform(0.01, 0.1) * span, rng.uniform(0.01, 0.1) * span,
+                      rng.uniform(0.05, 0.3) * span, rng.uniform(0.5, 1.2) * span]
+        elif kind == "s":
+            a[2:5] = [rng.uniform(1, 10) / span, rng.uniform(0, 0.3) * span, rng.uniform(0, 3) / span]
+        elif kind == "e":
+            td1 = rng.uniform(0, 0.3) * span
+            a[2:6] = [td1, rng.uniform(0.02, 0.2) * span, td1 + rng.uniform(0.1, 0.5) * span,
+                      rng.uniform(0.02, 0.2) * span]
+        else:
+            a[2:5] = [rng.uniform(1, 10) / span, rng.uniform(0, 5), rng.uniform(0.5, 5) / span]
+        for k in optional:
+            if rng.random() < 0.35:
+                a[k] = np.inf                              # omitted: the reference's default applies
+        cells = [C.c_double(float(v)) for v in a]
+        argv = (C.c_void_p * 7)(*[C.cast(C.pointer(c), C.c_void_p) for c in cells])
+        dc = C.c_void_p()
+        r = ref.waveformNew(None, C.byref(ctl), kind.encode(), argv, C.byref(dc))
+        assert r
+        assert ref.waveformInitialize(r) == 0
+        h = dev.devNew(tstop, ctl.reltol, ctl.chgtol, ctl.trtol, ctl.gmin)
+        args = np.ascontiguousarray(a)
+        for tm in np.concatenate(([0.0], np.sort(rng.uniform(0, tstop, 60)), [tstop])):
+            ctl.time = float(tm)
+            v0, n0 = C.c_double(), C.c_double(-7.0)
+            assert ref.waveformCalcValue(r, C.byref(v0)) == 0
+            assert ref.waveformNextStep(r, C.byref(n0)) == 0
+            v1, n1 = C.c_double(), C.c_double(-7.0)
+            dev.devWave(h, ord(kind), args.ctypes.data, float(tm), tstep, tstop, C.byref(v1), C.byref(n1))
+            assert _bits(v0.value) == _bits(v1.value), (kind, trial, tm, a.tolist(), v0.value, v1.value)
+            assert _bits(n0.value) == _bits(n1.value), (kind, trial, tm, a.tolist(), n0.value, n1.value)
+            compared += 1
+        dev.devFree(h)
+        _ = nargs
+    assert compared == 150 * 62
