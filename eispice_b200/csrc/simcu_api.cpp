@@ -1669,6 +1669,18 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	return 0;
 }
 
+/* test hook: the packed form of one table ([length][4]: x, y, slope or second
+ * derivative, x of the next point) exactly as the kernels read it */
+int simcuPackTable(const double *xy, int length, char type, double *packed)
+{
+	if (!xy || !packed || length < 1) return fail("simcuPackTable: bad arguments");
+	std::vector<double> out;
+	std::string err;
+	if (!packTable(xy, length, type, out, err)) return fail("%s", err.c_str());
+	std::memcpy(packed, out.data(), out.size() * sizeof(double));
+	return 0;
+}
+
 /* test hook: the symbolic analysis alone on caller-supplied matrices */
 int simcuSymbolic(int n, const int *colStart, const int *rowIdx, int numPilots,
 		const double *values, double threshold, int *pc, int *pr, int *numSlots,

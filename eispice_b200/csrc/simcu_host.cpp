@@ -398,6 +398,44 @@ bool Netlist::duplicate(const char *refdes) const
 /* ========================================================================== *
  * Flattening a netlist into the device program
  * ========================================================================== */
+/* One table in the packed form the kernels read: per point (x, y, m, x of the
+ * next point), m = slope to the next point (linear, piecewise.c:183-201) or
+ * second derivative of the natural cubic spline (piecewise.c:108-181), appended
+ * to out. */
+bool packTable(const double *xy, int n, char type, std::vector<double> &out, std::string &err)
+{
+	if (type == 'c' && n < 2) { err = "a spline table needs at least two points"; return false; }
+	std::vector<double> x(n), y(n), m(n, 0.0);
+	for (int i = 0; i < n; i++) { x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; }
+	for (int i = 0; i + 1 < n; i++)
+		if (x[i] > x[i + 1]) { err = "table x values must be sorted"; return false; }
+	if (type == 'l') {
+		for (int i = 0; i + 1 < n; i++) m[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+	} else if (n > 2) {
+		const int last = n - 1;
+		std::vector<double> h(last), b(last), u(last, 0.0), v(last, 0.0);
+		for (int i = 0; i < last; i++) {
+			h[i] = x[i + 1] - x[i];
+			b[i] = 6.0 * (y[i + 1] - y[i]) / h[i];
+		}
+		u[1] = 2.0 * h[0] + 2.0 * h[1];
+		v[1] = b[1] - b[0];
+		bool singular = (u[1] == 0.0);
+		for (int i = 2; i < last && !singular; i++) {
+			u[i] = 2.0 * h[i] + 2.0 * h[i - 1] - (h[i - 1] * h[i - 1] / u[i - 1]);
+			singular = (u[i] == 0.0);
+			v[i] = b[i] - b[i - 1] - (h[i - 1] * v[i - 1] / u[i - 1]);
+		}
+		if (singular) { err = "spline table is singular"; return false; }
+		for (int i = last - 1; i > 0; i--) m[i] = (v[i] - h[i] * m[i + 1]) / u[i];
+	}
+	for (int i = 0; i < n; i++) {
+		out.push_back(x[i]); out.push_back(y[i]); out.push_back(m[i]);
+		out.push_back((i + 1 < n) ? x[i + 1] : HUGE_VAL);
+	}
+	return true;
+}
+
 namespace {
 
 struct Flattener {
@@ -451,40 +489,10 @@ struct Flattener {
 	bool table(double **src, const int *len, char type, int &id, int klass = 2)
 	{
 		if (!src || !*src || !len || *len < 1) { err = "missing table"; return false; }
-		const int n = *len;
-		if (type == 'c' && n < 2) { err = "a spline table needs at least two points"; return false; }
-		const double *xy = *src;
 		id = (int)p.tabType.size();
-		std::vector<double> x(n), y(n), m(n, 0.0);
-		for (int i = 0; i < n; i++) { x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; }
-		for (int i = 0; i + 1 < n; i++)
-			if (x[i] > x[i + 1]) { err = "table x values must be sorted"; return false; }
-		if (type == 'l') {
-			for (int i = 0; i + 1 < n; i++) m[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
-		} else if (n > 2) {
-			const int last = n - 1;
-			std::vector<double> h(last), b(last), u(last, 0.0), v(last, 0.0);
-			for (int i = 0; i < last; i++) {
-				h[i] = x[i + 1] - x[i];
-				b[i] = 6.0 * (y[i + 1] - y[i]) / h[i];
-			}
-			u[1] = 2.0 * h[0] + 2.0 * h[1];
-			v[1] = b[1] - b[0];
-			bool singular = (u[1] == 0.0);
-			for (int i = 2; i < last && !singular; i++) {
-				u[i] = 2.0 * h[i] + 2.0 * h[i - 1] - (h[i - 1] * h[i - 1] / u[i - 1]);
-				singular = (u[i] == 0.0);
-				v[i] = b[i] - b[i - 1] - (h[i - 1] * v[i - 1] / u[i - 1]);
-			}
-			if (singular) { err = "spline table is singular"; return false; }
-			for (int i = last - 1; i > 0; i--) m[i] = (v[i] - h[i] * m[i + 1]) / u[i];
-		}
+		if (!packTable(*src, *len, type, p.tabP, err)) return false;
 		p.tabType.push_back(type);
 		p.tabClass.push_back(klass);
-		for (int i = 0; i < n; i++) {
-			p.tabP.push_back(x[i]); p.tabP.push_back(y[i]); p.tabP.push_back(m[i]);
-			p.tabP.push_back((i + 1 < n) ? x[i + 1] : HUGE_VAL);
-		}
 		p.tabOff.push_back((int)p.tabP.size() / 4);
 		return true;
 	}

@@ -93,6 +93,9 @@ struct Program {
 	int maxCalcStack = 0;
 };
 
+/* one table in the packed form the kernels read, appended to out: per point
+ * (x, y, m, x of the next point); type 'l' linear or 'c' natural cubic spline */
+bool packTable(const double *xy, int n, char type, std::vector<double> &out, std::string &err);
 /* flatten; M = instances.  false + err on failure */
 bool compileProgram(const Netlist &nl, int M, Program &p, std::string &err);
 /* re-read only the scalar parameters and tables (they are borrowed) */

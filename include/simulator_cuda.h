@@ -346,6 +346,10 @@ int simcuGetPivots(simcu_ *r, int phase, int *pc, int *pr);
  * stops after the source generation (no NVRTC). */
 int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source,
 		int *cubinBytes);
+/* test hook (no GPU needed): one table ([length][2]: x, y; type 'l' linear, 'c'
+ * natural cubic spline - math/piecewise.c:108-201) in the packed form the
+ * kernels read, packed[length][4] = x, y, slope / second derivative, next x */
+int simcuPackTable(const double *xy, int length, char type, double *packed);
 /* test hook: the symbolic analysis alone.  CSC pattern + numPilots value sets
  * ([numPilots][nnz]) in, pivot sequence, workspace slots and nnz(L+U-I) out */
 int simcuSymbolic(int n, const int *colStart, const int *rowIdx, int numPilots,

@@ -392,3 +392,97 @@ def test_source_waveforms_equal_the_references_waveform(tmp_path, kind):
         dev.devFree(h)
         _ = nargs
     assert compared == 150 * 62
+
+
+def _host_table_lib(tmp_path):
+    """pwSetIndex / pwCalcValueFn / pwGetNextX of the device library on packed tables."""
+    dev = open(DEVICE).read()
+    lookups = dev[dev.index("/* piecewise.c:44-67.  The cached index only shortens the walk;"):
+                  dev.index("/* ------------------------------------------------------------------------ *\n * Break-point test:")]
+    code = """
+#include <cmath>
+#define DEV static inline
+#define DEVFN static
+#define HUGE_VAL (__builtin_huge_val())
+struct Table { const double *p; int len; int type; };
+struct TabEntry { double x, y, m, xn; };
+static TabEntry tabLoad(const Table &t, int i)
+{
+	TabEntry e; const double *q = t.p + 4 * (size_t)i;
+	e.x = q[0]; e.y = q[1]; e.m = q[2]; e.xn = q[3];
+	return e;
+}
+%s
+extern "C" {
+void devTable(const double *packed, int len, int type, int *index, double x0, double *y, double *dydx, double *nextx)
+{
+	Table t; t.p = packed; t.len = len; t.type = type;
+	int i = *index;
+	pwCalcValue(t, i, x0, *y, *dydx);
+	int j = *index;
+	*nextx = pwGetNextX(t, j, x0);
+	*index = i;
+}
+}
+""" % lookups
+    cpp, so = tmp_path / "tab.cpp", tmp_path / "tab.so"
+    cpp.write_text(code)
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-o", str(so), str(cpp)],
+                   check=True)
+    lib = C.CDLL(str(so))
+    lib.devTable.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("kind", ["l", "c"])
+def test_table_lookups_equal_the_references_piecewise(tmp_path, kind):
+    """math/piecewise.c:44-67,96-263: linear and natural-cubic-spline tables as the
+    host packs them (simcuPackTable: slopes / second derivatives) and the device
+    looks them up (index walk from a cached index, value, slope, next corner) -
+    against piecewiseNew / Initialize / CalcValue / GetNextX of the reference."""
+    from eispice_b200 import engine
+    L = engine.lib()
+    L.simcuPackTable.argtypes = [C.c_void_p, C.c_int, C.c_char, C.c_void_p]
+    dev, ref = _host_table_lib(tmp_path), _reference()
+    ref.piecewiseNew.restype = C.c_void_p
+    ref.piecewiseNew.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char]
+    ref.piecewiseInitialize.argtypes = [C.c_void_p]
+    ref.piecewiseCalcValue.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    ref.piecewiseGetNextX.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    rng = np.random.default_rng(ord(kind))
+    compared = 0
+    for trial in range(120):
+        n = int(rng.integers(2 if kind == "l" else 3, 40))
+        x = np.cumsum(rng.uniform(0.01, 1.0, n)) * 10.0 ** rng.uniform(-10, 0) - rng.uniform(0, 2)
+        y = np.cumsum(rng.normal(size=n)) * 10.0 ** rng.uniform(-3, 1)
+        xy = np.ascontiguousarray(np.stack([x, y], axis=1))
+        packed = np.zeros((n, 4))
+        assert L.simcuPackTable(xy.ctypes.data, n, kind.encode(), packed.ctypes.data) == 0
+        data = C.c_void_p(xy.ctypes.data)
+        length = C.c_int(n)
+        r = ref.piecewiseNew(None, C.byref(data), C.byref(length), kind.encode())
+        assert r
+        assert ref.piecewiseInitialize(r) == 0
+        span = x[-1] - x[0]
+        i_ref, i_dev = C.c_int(0), C.c_int(0)
+        # a walk like a Newton loop's: small moves, occasional jumps, beyond both ends
+        q = x[0] + rng.uniform(-0.2, 1.2) * span
+        for k in range(80):
+            u = rng.random()
+            if u < 0.7:
+                q += rng.normal() * 0.05 * span
+            elif u < 0.85:
+                q = x[0] + rng.uniform(-0.3, 1.3) * span
+            else:
+                q = float(x[int(rng.integers(0, n))])              # exactly on a table point
+            y0, d0, nx0 = C.c_double(), C.c_double(), C.c_double()
+            j = C.c_int(i_ref.value)
+            assert ref.piecewiseCalcValue(r, C.byref(i_ref), q, C.byref(y0), C.byref(d0)) == 0
+            assert ref.piecewiseGetNextX(r, C.byref(j), q, C.byref(nx0)) == 0
+            y1, d1, nx1 = C.c_double(), C.c_double(), C.c_double()
+            dev.devTable(packed.ctypes.data, n, ord(kind), C.byref(i_dev), q, C.byref(y1), C.byref(d1), C.byref(nx1))
+            assert i_ref.value == i_dev.value, (kind, trial, k, q)
+            assert _bits(y0.value) == _bits(y1.value) and _bits(d0.value) == _bits(d1.value), (kind, trial, k, q, y0.value, y1.value)
+            assert _bits(nx0.value) == _bits(nx1.value), (kind, trial, k, q, nx0.value, nx1.value)
+            compared += 1
+    assert compared == 120 * 80
