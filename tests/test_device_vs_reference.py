@@ -486,3 +486,107 @@ def test_table_lookups_equal_the_references_piecewise(tmp_path, kind):
             assert _bits(nx0.value) == _bits(nx1.value), (kind, trial, k, q, nx0.value, nx1.value)
             compared += 1
     assert compared == 120 * 80
+
+
+def test_tline_history_lookup_equals_the_references_history_interp(tmp_path):
+    """core/history.c:36-59 + math/history_interp.c:42-92 on the reference's own
+    linked list of accepted records against the kernel's ring: galloping + binary
+    search from a hint (tlineLocateFn) and the interpolation / extrapolation of a
+    record column (tlineInterp).  Same value, bit for bit; the same lookups fail.
+    (At or past the newest record the reference itself crashes, see below.)"""
+    dev_src = open(DEVICE).read()
+    body = dev_src[dev_src.index("DEV int tlineWrap(int p, int R)"):dev_src.index("#ifdef SIMCU_JIT\n/* First pass over the T-lines")]
+    code = """
+#include <cstddef>
+#define DEV static inline
+#define DEVFN static
+struct int4 { int x, y, z, w; };
+%s
+extern "C" int lookup(const double *times, const double *vals, int nh, int R, int count, int *hint, double tp,
+		int col, double *out)
+{
+	const int4 r = tlineLocateFn(times, R, count, *hint, tp);
+	if (!r.w) return -1;
+	*hint = r.x;
+	*out = tlineInterp(vals + (size_t)r.y * nh, vals + (size_t)r.z * nh, col, times[r.y], times[r.z], tp);
+	return 0;
+}
+""" % body
+    cpp, so = tmp_path / "hist.cpp", tmp_path / "hist.so"
+    cpp.write_text(code)
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-o", str(so), str(cpp)],
+                   check=True)
+    dev = C.CDLL(str(so))
+    dev.lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_int,
+                           C.c_void_p]
+    ref = _reference()
+    ref.listNew.restype = C.c_void_p
+    ref.listNew.argtypes = [C.c_void_p]
+    ref.listAdd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    ref.historyNew.restype = C.c_void_p
+    ref.historyNew.argtypes = [C.c_double, C.c_void_p, C.c_int, C.c_uint]
+    ref.historyInterpNew.restype = C.c_void_p
+    ref.historyInterpNew.argtypes = [C.c_void_p, C.c_void_p]
+    ref.historyInterpInitialize.argtypes = [C.c_void_p]
+    ref.historyInterpSetTime.argtypes = [C.c_void_p, C.c_double]
+    ref.historyInterpGetData.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(33)
+    same = failed = past = 0
+    nh = 5
+    for trial in range(60):
+        count = int(rng.integers(1, 120))
+        R = count + int(rng.integers(0, 8))                 # nothing has left the ring
+        t = np.concatenate(([0.0], np.cumsum(10.0 ** rng.uniform(-15, -10, count))))[:count]
+        vals = np.ascontiguousarray(np.cumsum(rng.normal(size=(count, nh)), axis=0))
+        ring_t = np.zeros(R)
+        ring_v = np.zeros((R, nh))
+        ring_t[:count], ring_v[:count] = t, vals
+        lst = ref.listNew(None)
+        for q in range(count):
+            rec = ref.historyNew(float(t[q]), vals[q].ctypes.data, nh, 0)
+            assert rec and ref.listAdd(lst, rec, None) == 0
+        hi = ref.historyInterpNew(None, lst)
+        assert hi and ref.historyInterpInitialize(hi) == 0
+        hint = C.c_int(0)
+        tp = 0.0
+        for k in range(80):
+            u = rng.random()
+            if u < 0.6:                                   # the delayed time creeps forward, as in a run
+                tp = tp + 10.0 ** rng.uniform(-14, -10.5)
+            elif u < 0.8:
+                tp = float(rng.uniform(0.0, t[-1] * 1.1 + 1e-13))
+            elif u < 0.9:
+                tp = float(t[int(rng.integers(0, count))])
+            else:
+                tp = -float(rng.uniform(0, 1e-12))        # before the first record
+            col = int(rng.integers(0, nh))
+            want = C.c_double()
+            if tp >= t[-1]:
+                # At / past the newest record the reference means to use the last two
+                # records (history_interp.c:58-61) but its listNodeGetNext dereferences
+                # the missing next node (libs/data/list.c:75-84) and crashes: the
+                # intended rule is checked against its formula instead.
+                if count < 2:
+                    rc0 = -1
+                else:
+                    tP, tN, xP, xN = t[-2], t[-1], vals[-2, col], vals[-1, col]
+                    want.value = ((xN - xP) / (tN - tP)) * (tp - tP) + xP
+                    rc0 = 0
+                    past += 1
+            else:
+                ref.ref_shim_quiet(1)
+                rc0 = ref.historyInterpSetTime(hi, tp)
+                if rc0 == 0:
+                    rc0 = ref.historyInterpGetData(hi, col + 1, C.byref(want))
+                ref.ref_shim_quiet(0)
+            got = C.c_double()
+            rc1 = dev.lookup(ring_t.ctypes.data, ring_v.ctypes.data, nh, R, count, C.byref(hint), tp, col,
+                             C.byref(got))
+            assert (rc0 != 0) == (rc1 != 0), (trial, k, tp, count, rc0, rc1)
+            if rc0 == 0:
+                assert _bits(want.value) == _bits(got.value), (trial, k, tp, want.value, got.value)
+                same += 1
+            else:
+                failed += 1
+                assert ref.historyInterpInitialize(hi) == 0       # the reference forgets its node on error
+    assert same > 3000 and failed > 50 and past > 100
