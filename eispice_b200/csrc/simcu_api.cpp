@@ -1669,6 +1669,52 @@ int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source, in
 	return 0;
 }
 
+/* test hook (no GPU needed): the host-side arrays a launch of the specialised
+ * kernel reads - what Prepare / Upload copy to the device - by name: "pmap" (int),
+ * "pconst", "pinst", "tabP" (double), "iinst", "tabDesc" (int), "control" (one
+ * SimcuControl with the run constants of core/simulator.c:91-109 resolved for this
+ * tstep / tstop / tmax).  *data receives a malloc'd copy (simcuFree), *bytes its
+ * size.  tests/ runs the generated translation unit compiled for the host on
+ * these arrays and compares it with the oracle; the product never reads them
+ * back. */
+int simcuDebugProgram(simcu_ *r, const char *what, double tstep, double tstop, double tmax,
+		void **data, int *bytes)
+{
+	if (!r || !what || !data || !bytes) return -1;
+	if (ensureCompiled(r)) return -1;
+	const Program &p = r->prog;
+	const std::string w(what);
+	const void *src = nullptr;
+	size_t n = 0;
+	std::vector<int> desc;
+	SimcuControl c = r->ctl;
+	if (w == "pmap") { src = p.pmap.data(); n = p.pmap.size() * sizeof(int); }
+	else if (w == "pconst") { src = p.pconst.data(); n = p.pconst.size() * sizeof(double); }
+	else if (w == "pinst") { src = p.pinst.data(); n = p.pinst.size() * sizeof(double); }
+	else if (w == "iinst") { src = p.iinst.data(); n = p.iinst.size() * sizeof(int); }
+	else if (w == "tabP") { src = p.tabP.data(); n = p.tabP.size() * sizeof(double); }
+	else if (w == "tabDesc") {
+		const int ntab = (int)p.tabType.size();
+		desc.assign((size_t)4 * std::max(1, ntab), -1);
+		for (int t = 0; t < ntab; t++) {
+			desc[4 * t] = p.tabOff[t]; desc[4 * t + 1] = p.tabOff[t + 1] - p.tabOff[t];
+			desc[4 * t + 2] = p.tabType[t]; desc[4 * t + 3] = -1;
+		}
+		src = desc.data(); n = desc.size() * sizeof(int);
+	} else if (w == "control") {
+		if (!(tstep > 0.0) || !(tstop > 0.0)) return fail("tstep and tstop must be positive");
+		if (tmax == 0.0) { tmax = tstop / 50; tmax = (tstep < tmax) ? tstep : tmax; }
+		c.tstep = tstep; c.tstop = tstop; c.tmax = tmax;
+		c.minstep = (r->minstepOpt < 0) ? tstep * 5e-5 : r->minstepOpt;
+		src = &c; n = sizeof c;
+	} else return fail("simcuDebugProgram: unknown array %s", what);
+	*data = std::malloc(n ? n : 1);
+	if (!*data) return -1;
+	if (n) std::memcpy(*data, src, n);
+	*bytes = (int)n;
+	return 0;
+}
+
 /* test hook: the packed form of one table ([length][4]: x, y, slope or second
  * derivative, x of the next point) exactly as the kernels read it */
 int simcuPackTable(const double *xy, int length, char type, double *packed)

@@ -346,6 +346,14 @@ int simcuGetPivots(simcu_ *r, int phase, int *pc, int *pr);
  * stops after the source generation (no NVRTC). */
 int simcuCompileOnly(simcu_ *r, char *probes[], int numProbes, char **source,
 		int *cubinBytes);
+/* test hook (no GPU needed): a malloc'd copy (simcuFree) of one of the host-side
+ * arrays a launch of the specialised kernel reads, by name: "pmap", "iinst",
+ * "tabDesc" (int), "pconst", "pinst", "tabP" (double), "control" (the
+ * SimcuControl of csrc/simcu_program.h with the run constants of
+ * core/simulator.c:91-109 resolved for tstep / tstop / tmax).  tests/ runs the
+ * generated translation unit compiled for the host on them against the oracle. */
+int simcuDebugProgram(simcu_ *r, const char *what, double tstep, double tstop, double tmax,
+		void **data, int *bytes);
 /* test hook (no GPU needed): one table ([length][2]: x, y; type 'l' linear, 'c'
  * natural cubic spline - math/piecewise.c:108-201) in the packed form the
  * kernels read, packed[length][4] = x, y, slope / second derivative, next x */

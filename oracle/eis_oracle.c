@@ -1007,6 +1007,9 @@ struct eo_sim {
 	int linN, linCap; int *linMask;
 	/* stamp watch (tests only): which A entries / B rows differed between two
 	 * consecutive solves of ONE simulatorSolve loop, per phase */
+	/* pivots of the FIRST factorisation of each phase of the last run (tests only) */
+	int *firstPc[2], *firstPr[2];
+	int firstSeen[2];
 	int watchOn;
 	double *watchA, *watchB;        /* stamps at the previous solve of this loop */
 	char *changedA[2], *changedB[2];
@@ -1130,6 +1133,7 @@ void eoDestroy(eo_sim *s)
 	free(s->logTime); free(s->logFlag); free(s->linMask);
 	free(s->watchA); free(s->watchB);
 	for (i = 0; i < 2; i++) { free(s->changedA[i]); free(s->changedB[i]); }
+	for (i = 0; i < 2; i++) { free(s->firstPc[i]); free(s->firstPr[i]); }
 	free(s);
 }
 void eoFree(void *p) { free(p); }
@@ -1824,6 +1828,15 @@ static int luSolve(eo_sim *s)
 		s->X[s->pcol[k]] = acc * s->pinv[k];
 	}
 	if (s->phase) s->st.factorizations++; else s->st.op_factorizations++;
+	if (!s->firstSeen[s->phase]) {       /* eoGetPivots */
+		if (s->firstPc[s->phase] == NULL) {
+			s->firstPc[s->phase] = malloc(sizeof(int) * (N + 1));
+			s->firstPr[s->phase] = malloc(sizeof(int) * (N + 1));
+		}
+		memcpy(s->firstPc[s->phase], s->pcol, sizeof(int) * N);
+		memcpy(s->firstPr[s->phase], s->prow, sizeof(int) * N);
+		s->firstSeen[s->phase] = 1;
+	}
 	return 0;
 }
 
@@ -2034,6 +2047,16 @@ static void logAttempt(eo_sim *s, double time, int order, int outcome, int solve
 }
 
 void eoSetAttemptLog(eo_sim *s, int on) { s->logOn = on; s->logN = 0; s->linN = 0; }
+
+/* the (column, row) sequence of the first factorisation of a phase in the runs so
+ * far (partial pivoting unless a fixed sequence is being replayed) */
+int eoGetPivots(eo_sim *s, int phase, int *pc, int *pr)
+{
+	if (phase < 0 || phase > 1 || !s->firstSeen[phase]) return -1;
+	memcpy(pc, s->firstPc[phase], sizeof(int) * s->N);
+	memcpy(pr, s->firstPr[phase], sizeof(int) * s->N);
+	return s->N;
+}
 
 void eoSetStampWatch(eo_sim *s, int on) { s->watchOn = on; }
 

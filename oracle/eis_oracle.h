@@ -67,6 +67,12 @@ int eoSetParam(eo_sim *s, const char *refdes, const char *name, double v);
  * phase 0 = operating point, 1 = transient. */
 int eoSetPivots(eo_sim *s, int phase, const int *pc, const int *pr, int n);
 
+/* (column, row) of every elimination step of the FIRST factorisation of a phase
+ * since the simulator was created: the sequence a test hands to the engine
+ * (simcuSetPivots) and back to eoSetPivots so both sides eliminate alike.
+ * Returns N, or -1 if that phase has not been solved yet. */
+int eoGetPivots(eo_sim *s, int phase, int *pc, int *pr);
+
 /* Attempt log of the last transient (test instrumentation, see eis_oracle.c):
  * one entry per attempt in order - the time tried and a flag word
  * order | outcome << 4 | solves << 8, outcome 0 accepted / 1 LTE reject /

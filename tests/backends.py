@@ -76,6 +76,7 @@ def oracle_lib():
         lib.eoSetAttemptLog.argtypes = [C.c_void_p, C.c_int]
         lib.eoGetAttemptLog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.eoGetLinearizeLog.argtypes = [C.c_void_p, C.c_void_p]
+        lib.eoGetPivots.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.eoSetStampWatch.argtypes = [C.c_void_p, C.c_int]
         lib.eoGetStampWatch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _oracle = lib
@@ -232,6 +233,15 @@ class OracleSim:
         if n == 0:
             return np.zeros(0, dtype=np.int32)
         return np.ctypeslib.as_array(m, shape=(n,)).copy()
+
+    def first_pivots(self, phase):
+        """(pc, pr) of the first factorisation of a phase in the runs so far."""
+        n = self.lib.eoNumUnknowns(self.h)
+        pc = np.zeros(n, dtype=np.int32)
+        pr = np.zeros(n, dtype=np.int32)
+        if self.lib.eoGetPivots(self.h, phase, pc.ctypes.data, pr.ctypes.data) < 0:
+            return None
+        return pc, pr
 
     def watch_stamps(self, on=True):
         self.lib.eoSetStampWatch(self.h, 1 if on else 0)
