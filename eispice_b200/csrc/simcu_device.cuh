@@ -473,9 +473,15 @@ DEV double DD3(double xnp1, double xn, double x1, double x2, double hn, double h
  * slot a steps behind the current one; a = 3 of the time ring is the "next"
  * slot that holds the time of the present attempt.  The reference's negative
  * ring index while the counter is below a (integrator.c:90-96, (n-a) % 4 < 0)
- * lands on the same age of the previous ring; AGEQ reproduces that. */
+ * lands on the same age of the previous ring; AGEQ reproduces that.
+ * For the f ring that is age a of the y ring, read only while the counter is
+ * below a - and until then that slot still holds the 0 of itInitialize (a value
+ * needs a advances to get there): AGEQF reads the constant, and ages 1 and 2 of
+ * the y ring are neither stored nor rotated (integrator.c never reads y[] at
+ * any other index than the current one). */
 #define AGE(c, sb, k, a) (c).S((sb) + 2 + (k) * 4 + (a))
 #define AGEQ(c, sb, k, a, nn) (((nn) >= (a)) ? AGE(c, sb, k, a) : AGE(c, sb, (k) - 1, a))
+#define AGEQF(c, sb, a, nn) (((nn) >= (a)) ? AGE(c, sb, RF, a) : 0.0)
 enum { RT = 0, RH = 1, RX = 2, RY = 3, RF = 4 };
 
 DEV void itInitialize(const Inst &c, int sb, int ib, double ic, double ydtdx)
@@ -486,8 +492,9 @@ DEV void itInitialize(const Inst &c, int sb, int ib, double ic, double ydtdx)
 	SIMCU_UNROLL
 	for (int j = 0; j < 4; j++) {
 		c.itT[j] = 0.0;
-		AGE(c, sb, RY, j) = 0.0; AGE(c, sb, RX, j) = ic; AGE(c, sb, RF, j) = ydtdx;
+		AGE(c, sb, RX, j) = ic; AGE(c, sb, RF, j) = ydtdx;
 	}
+	AGE(c, sb, RY, 0) = 0.0;
 	SIMCU_UNROLL
 	for (int j = 0; j < 3; j++) c.itH[j] = W_TSTOP(c);
 }
@@ -516,17 +523,15 @@ DEV void itIntegrate(Inst &c, int sb, int ib, double x0, double ydtdx,
 	if (isnan(x0)) { c.err = SIMCU_ERR_NAN; return; }
 	const int nn = c.itN;
 	if (c.itAdv) {
-		SIMCU_UNROLL
-		for (int k = RX; k <= RF; k++) {
-			AGE(c, sb, k, 2) = AGE(c, sb, k, 1); AGE(c, sb, k, 1) = AGE(c, sb, k, 0);
-		}
+		AGE(c, sb, RX, 2) = AGE(c, sb, RX, 1); AGE(c, sb, RX, 1) = AGE(c, sb, RX, 0);
+		AGE(c, sb, RF, 2) = AGE(c, sb, RF, 1); AGE(c, sb, RF, 1) = AGE(c, sb, RF, 0);
 	}
 	const double h = c.itH[0];
 	AGE(c, sb, RX, 0) = x0;
 	const double yn = ADD_RN(MUL_RN(c.S(sb + 1), x0), -c.S(sb));
 	AGE(c, sb, RY, 0) = yn;
 	AGE(c, sb, RF, 0) = ydtdx;
-	const double fp = AGEQ(c, sb, RF, 1, nn);
+	const double fp = AGEQF(c, sb, 1, nn);
 	if (c.order < 2) {
 		dydx0 = fp / h;
 		y0 = dydx0 * x0;
@@ -575,7 +580,7 @@ DEV double itNextStep(Inst &c, int sb, int ib, double x0, double ydtdx, double a
 	const double h1 = (nn >= 1) ? c.itH[1] : c.itT[1], h2 = (nn >= 2) ? c.itH[2] : c.itT[2];
 	const double h = itNextStepFn(c.order, k.reltol, k.chgtol, k.trtol, abstol, x0, ydtdx,
 			c.S(sb), c.S(sb + 1), AGE(c, sb, RY, 0), c.itH[0], AGE(c, sb, RX, 0),
-			AGE(c, sb, RF, 0), AGEQ(c, sb, RF, 1, nn), x1, h1, AGEQ(c, sb, RF, 2, nn), x2, h2);
+			AGE(c, sb, RF, 0), AGEQF(c, sb, 1, nn), x1, h1, AGEQF(c, sb, 2, nn), x2, h2);
 	if (isnan(h)) c.err = SIMCU_ERR_NAN;
 	return h;
 }
@@ -1238,6 +1243,19 @@ DEV int devStep(Inst &c, const int *d, const int *bv = nullptr)
 	}
 }
 
+/* The companion model stamped at the previous attempt (the devices' G and Ieq,
+ * capacitor.c:101-108) is what the integrator itself keeps as its last dydx0 and
+ * y0 (integrator.c:158-160): both are 0 until the first integration and are
+ * written together from the same numbers.  The specialised kernel reads the
+ * integrator's pair and stores nothing twice. */
+#ifdef SIMCU_JIT
+#define COMPANION_OLD(c, sb, g, i) const double g = (c).S((sb) + 3), i = (c).S((sb) + 2)
+#define COMPANION_KEEP(c, sb, g, i) ((void)0)
+#else
+#define COMPANION_OLD(c, sb, g, i) const double g = (c).S(sb), i = (c).S((sb) + 1)
+#define COMPANION_KEEP(c, sb, g, i) do { (c).S(sb) = (g); (c).S((sb) + 1) = (i); } while (0)
+#endif
+
 DEV void devIntegrate(Inst &c, const int *d)
 {
 	const int type = d[DF_TYPE], sb = d[DF_SBASE], ib = d[DF_IBASE];
@@ -1246,25 +1264,25 @@ DEV void devIntegrate(Inst &c, const int *d)
 	case DK_C: case DK_BC: {                    /* capacitor.c:76-108, nonlinear_c.c:232-277 */
 		const double x0 = c.X(d[DF_K]) - c.X(d[DF_J]);
 		const double cap = (type == DK_C) ? c.P(d[DF_P0]) : c.S(sb + 24);
+		COMPANION_OLD(c, sb, Gold, Iold);
 		itIntegrate(c, sb + 2, ib, x0, cap, G, Ieq);
 		if (c.err) return;
 		const int *s = (type == DK_C) ? d + DF_A0 : d + DF_BA0;   /* KK KJ JK JJ */
-		const double dG = G - c.S(sb);
+		const double dG = G - Gold;
 		c.Aplus(s[0], dG); c.Aplus(s[1], -dG); c.Aplus(s[2], -dG); c.Aplus(s[3], dG);
-		c.S(sb) = G;
-		const double dI = Ieq - c.S(sb + 1);
+		const double dI = Ieq - Iold;
 		c.Bplus(d[DF_K], dI); c.Bplus(d[DF_J], -dI);
-		c.S(sb + 1) = Ieq;
+		COMPANION_KEEP(c, sb, G, Ieq);
 		break;
 	}
 	case DK_L: {                                /* inductor.c:78-109 */
 		const double x0 = c.X(d[DF_ROWR]);
+		COMPANION_OLD(c, sb, Gold, Iold);
 		itIntegrate(c, sb + 2, ib, x0, c.P(d[DF_P0]), G, Ieq);
 		if (c.err) return;
-		c.Aplus(d[DF_A0 + 4], -(G - c.S(sb)));
-		c.S(sb) = G;
-		c.Bplus(d[DF_ROWR], -(Ieq - c.S(sb + 1)));
-		c.S(sb + 1) = Ieq;
+		c.Aplus(d[DF_A0 + 4], -(G - Gold));
+		c.Bplus(d[DF_ROWR], -(Ieq - Iold));
+		COMPANION_KEEP(c, sb, G, Ieq);
 		break;
 	}
 	default: break;
