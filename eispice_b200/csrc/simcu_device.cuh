@@ -473,14 +473,13 @@ DEV double DD3(double xnp1, double xn, double x1, double x2, double hn, double h
  * slot a steps behind the current one; a = 3 of the time ring is the "next"
  * slot that holds the time of the present attempt.  The reference's negative
  * ring index while the counter is below a (integrator.c:90-96, (n-a) % 4 < 0)
- * lands on the same age of the previous ring; AGEQ reproduces that.
+ * lands on the same age of the previous ring.
  * For the f ring that is age a of the y ring, read only while the counter is
  * below a - and until then that slot still holds the 0 of itInitialize (a value
  * needs a advances to get there): AGEQF reads the constant, and ages 1 and 2 of
  * the y ring are neither stored nor rotated (integrator.c never reads y[] at
  * any other index than the current one). */
 #define AGE(c, sb, k, a) (c).S((sb) + 2 + (k) * 4 + (a))
-#define AGEQ(c, sb, k, a, nn) (((nn) >= (a)) ? AGE(c, sb, k, a) : AGE(c, sb, (k) - 1, a))
 #define AGEQF(c, sb, a, nn) (((nn) >= (a)) ? AGE(c, sb, RF, a) : 0.0)
 enum { RT = 0, RH = 1, RX = 2, RY = 3, RF = 4 };
 
@@ -575,7 +574,7 @@ DEV double itNextStep(Inst &c, int sb, int ib, double x0, double ydtdx, double a
 	const int nn = c.itN;
 	(void)ib;
 	/* below the counter the reference reads the same age of the PREVIOUS ring
-	 * (AGEQ): x <- h, h <- t, f <- y */
+	 * (x <- h, h <- t; f <- y, i.e. AGEQF) */
 	const double x1 = (nn >= 1) ? AGE(c, sb, RX, 1) : c.itH[1], x2 = (nn >= 2) ? AGE(c, sb, RX, 2) : c.itH[2];
 	const double h1 = (nn >= 1) ? c.itH[1] : c.itT[1], h2 = (nn >= 2) ? c.itH[2] : c.itT[2];
 	const double h = itNextStepFn(c.order, k.reltol, k.chgtol, k.trtol, abstol, x0, ydtdx,
