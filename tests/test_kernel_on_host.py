@@ -62,7 +62,9 @@ DRIVER = r"""
 extern "C" int runKernel(int M, int ngrid, int nprobes, int histRecords, int rawMaxPoints,
 		const SimcuControl *ctl, const int *pmap, const double *pconst, const double *pinst,
 		const int *iinst, const double *tabP, const int *tabDesc, double *Ht, double *Hx,
-		double *outGrid, double *outRaw, int *CI, double *outMeasure, int opOnly)
+		double *outGrid, double *outRaw, int *CI, double *outMeasure, int opOnly,
+		const int *replayOff, const double *replayTime, const int *replayFlag, const int *replayLinOff,
+		const int *replayLin)
 {
 	SimcuArgs a;
 	std::memset(&a, 0, sizeof a);
@@ -74,6 +76,8 @@ extern "C" int runKernel(int M, int ngrid, int nprobes, int histRecords, int raw
 	a.rawMaxPoints = rawMaxPoints; a.rawFirst = 0; a.rawCount = M; a.outRaw = outRaw;
 	a.CI = CI; a.outMeasure = outMeasure;
 	a.maxAttempts = LLONG_MAX;
+	a.replayOff = replayOff; a.replayTime = replayTime; a.replayFlag = replayFlag;
+	a.replayLinOff = replayLinOff; a.replayLin = replayLin;
 	int counter = 0;
 	a.counter = &counter;
 	a.lanes = 1; a.count = M; a.claimBelow = 31;       /* one lane claims instance after instance */
@@ -94,7 +98,8 @@ def _debug_array(eng, what, dtype, tstep=1.0, tstop=1.0):
     return arr if arr.size else np.zeros(1, dtype=dtype)
 
 
-def _run_on_host(tmp_path, tag, nl, M, params, probes, tstep, tstop, pivots, op_only=False, options=None):
+def _run_on_host(tmp_path, tag, nl, M, params, probes, tstep, tstop, pivots, op_only=False, options=None,
+                 replay=None):
     """Raw records [instance][point][1 + N] of the generated kernel run on the host."""
     eng = engine.Engine(nl, M)
     for k, v in (options or {}).items():
@@ -114,7 +119,7 @@ def _run_on_host(tmp_path, tag, nl, M, params, probes, tstep, tstop, pivots, op_
     subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-fpermissive", "-shared", "-fPIC", "-o", str(so),
                     str(cpp)], check=True)
     lib = C.CDLL(str(so))
-    lib.runKernel.argtypes = [C.c_int] * 5 + [C.c_void_p] * 13 + [C.c_int]
+    lib.runKernel.argtypes = [C.c_int] * 5 + [C.c_void_p] * 13 + [C.c_int] + [C.c_void_p] * 5
     nh = int(__import__("re").search(r"#define SIMCU_NH (\d+)", src).group(1))
     ng = int(np.floor(tstop / tstep * (1.0 + 1e-12))) + 1
     if (ng - 1) * tstep < tstop * (1.0 - 1e-9):
@@ -131,9 +136,12 @@ def _run_on_host(tmp_path, tag, nl, M, params, probes, tstep, tstop, pivots, op_
     p = lambda a: a.ctypes.data
     claimed = lib.runKernel(M, ng, len(probes), R, raw_max, p(ctl), p(arrays["pmap"]), p(arrays["pconst"]),
                             p(arrays["pinst"]), p(arrays["iinst"]), p(arrays["tabP"]), p(arrays["tabDesc"]),
-                            p(Ht), p(Hx), p(out_grid), p(out_raw), p(CI), p(meas), 1 if op_only else 0)
+                            p(Ht), p(Hx), p(out_grid), p(out_raw), p(CI), p(meas), 1 if op_only else 0,
+                            *([p(x) for x in replay] if replay else [None] * 5))
     assert claimed == M + 1                       # M instances + the claim that found the queue empty
     status, npts = CI[1], CI[8]                   # CI_STATUS, CI_NPTS (simcu_program.h)
+    if replay:
+        return [out_raw[:npts[i], :, i] for i in range(M)], status, CI[13] + CI[15]   # CI_REPLAY_DIFF + CI_LIN_DIFF
     return [out_raw[:npts[i], :, i] for i in range(M)], status, out_grid[:ng]
 
 
@@ -218,3 +226,38 @@ def test_kernel_options_do_not_change_a_bit_on_the_host(name, options, tmp_path)
     for i, (inl, vi_set) in enumerate(instances):
         _, want = _oracle(inl, vi_set, w.tstep, w.tstop, pivots)
         assert np.array_equal(raw[i], want), (name, options, i)
+
+
+@pytest.mark.parametrize("name", ["cfg5", "cfg4", "cfg2"])
+def test_replay_kernel_on_the_host_follows_the_oracle_log_without_a_disagreement(name, tmp_path):
+    """The kernel compiled with option replay takes every accept / reject decision
+    and every convergence-test outcome from the oracle's log (what
+    tests/test_gpu_replay.py does on the GPU) - and, walking the same numbers,
+    would have decided the same each time: zero disagreements, same records."""
+    M = 2
+    w = workloads.make(name, M)
+    instances = [w.instance_netlist(i) for i in range(M)]
+    first, _ = _oracle(instances[0][0], instances[0][1], w.tstep, w.tstop)
+    pivots = [first.first_pivots(0), first.first_pivots(1)]
+    logs, want = [], []
+    for inl, vi_set in instances:
+        ora = backends.OracleSim(inl, vi_set)
+        for phase, pv in enumerate(pivots):
+            ora.set_pivots(phase, pv[0], pv[1])
+        ora.log_attempts()
+        data, _ = ora.tran(w.tstep, w.tstop)
+        t, f = ora.attempt_log()
+        logs.append((t, f, ora.linearize_log()))
+        want.append(data)
+    off = np.zeros(M + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(x[0]) for x in logs])
+    loff = np.zeros(M + 1, dtype=np.int32)
+    loff[1:] = np.cumsum([len(x[2]) for x in logs])
+    replay = [off, np.ascontiguousarray(np.concatenate([x[0] for x in logs])),
+              np.ascontiguousarray(np.concatenate([x[1] for x in logs]).astype(np.int32)), loff,
+              np.ascontiguousarray(np.concatenate([x[2] for x in logs]).astype(np.int32))]
+    raw, status, diffs = _run_on_host(tmp_path, name, w.cct.netlist(), M, w.params, w.probes, w.tstep, w.tstop,
+                                      pivots, options={"replay": 1}, replay=replay)
+    assert (status == 0).all() and (diffs == 0).all(), (status, diffs)
+    for i in range(M):
+        assert np.array_equal(raw[i], want[i]), (name, i)
